@@ -1,0 +1,140 @@
+"""oracle/oracle_py.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes view of oracle/liboracle.so (the CPU restatement of the reference's
+cpuLS.hpp receive path) plus a runner for the reference-built binaries in
+oracle/_ref/.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS: dict[str, ctypes.CDLL] = {}
+
+
+def build(fast: bool = False, ref: bool = True) -> None:
+    """Compile the oracle (and, when /root/reference exists, oracle/_ref)."""
+    targets = ["liboracle.so", "liboracle_fast.so"]
+    subprocess.run(["make", "-C", _HERE, "--no-print-directory", *targets], check=True,
+                   stdout=subprocess.DEVNULL)
+    if ref and os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", _HERE, "--no-print-directory", "ref"], check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+def _lib(fast: bool = False) -> ctypes.CDLL:
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name not in _LIBS:
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
+        lib = ctypes.CDLL(path)
+        lib.oracle_bits_row_bytes.restype = ctypes.c_size_t
+        lib.oracle_bits_row_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        lib.oracle_demod_frames.restype = ctypes.c_int
+        lib.oracle_demod_frames.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + \
+            [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        lib.oracle_fft_f32.restype = None
+        lib.oracle_fft_f32.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.oracle_pilot_to_bin_order.restype = None
+        lib.oracle_pilot_to_bin_order.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.oracle_shift_one_row.restype = None
+        lib.oracle_shift_one_row.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.oracle_demap_row.restype = None
+        lib.oracle_demap_row.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]
+        _LIBS[name] = lib
+    return _LIBS[name]
+
+
+def bits_row_bytes(K: int, qam_bits: int) -> int:
+    return (K * qam_bits + 7) // 8
+
+
+def fft_f32(x: np.ndarray, sign: int = -1) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    out = np.empty_like(x)
+    _lib().oracle_fft_f32(x.shape[-1], x.ctypes.data, out.ctypes.data, sign)
+    return out
+
+
+def pilot_to_bin_order(p_asc: np.ndarray) -> np.ndarray:
+    p_asc = np.ascontiguousarray(p_asc, dtype=np.complex64)
+    out = np.empty_like(p_asc)
+    _lib().oracle_pilot_to_bin_order(p_asc.ctypes.data, out.ctypes.data, p_asc.shape[0])
+    return out
+
+
+def shift_one_row(row: np.ndarray) -> np.ndarray:
+    out = np.array(row, dtype=np.complex64, copy=True, order="C")
+    _lib().oracle_shift_one_row(out.ctypes.data, out.shape[0])
+    return out
+
+
+def demap_row(sym: np.ndarray, qam_bits: int):
+    sym = np.ascontiguousarray(sym, dtype=np.complex64)
+    K = sym.shape[0]
+    packed = np.zeros(bits_row_bytes(K, qam_bits), dtype=np.uint8)
+    idx = np.zeros(K, dtype=np.uint8)
+    _lib().oracle_demap_row(sym.ctypes.data, K, qam_bits, packed.ctypes.data, idx.ctypes.data)
+    return packed, idx
+
+
+def demod_frames(rx: np.ndarray, pilot_asc: np.ndarray, qam_bits: int, cp: int,
+                 n_threads: int = 1, fast: bool = False, want_bits: bool = True):
+    """rx [F][S][A][N+C] complex64 -> dict(hconj [F,A,K], hsqrd [F,K], combined [F,S-1,K], bits)."""
+    rx = np.ascontiguousarray(rx, dtype=np.complex64)
+    F, S, A, NC = rx.shape
+    N = NC - cp
+    K = N - 1
+    pilot_asc = np.ascontiguousarray(pilot_asc, dtype=np.complex64)
+    assert pilot_asc.shape == (K,)
+    hconj = np.empty((F, A, K), np.complex64)
+    hsqrd = np.empty((F, K), np.float32)
+    comb = np.empty((F, S - 1, K), np.complex64)
+    bits = np.zeros((F, S - 1, bits_row_bytes(K, qam_bits)), np.uint8)
+    rc = _lib(fast).oracle_demod_frames(rx.ctypes.data, pilot_asc.ctypes.data, F, S, A, N, cp,
+                                        qam_bits, hconj.ctypes.data, hsqrd.ctypes.data,
+                                        comb.ctypes.data, bits.ctypes.data if want_bits else None,
+                                        n_threads)
+    if rc != 0:
+        raise ValueError(f"oracle_demod_frames rc={rc}")
+    return {"hconj": hconj, "hsqrd": hsqrd, "combined": comb, "bits": bits}
+
+
+def ref_case_name(A: int, N: int, C: int, S: int) -> str:
+    return f"A{A}_N{N}_C{C}_S{S}"
+
+
+def ref_binary(A: int, N: int, C: int, S: int):
+    p = os.path.join(_HERE, "_ref", "cpuls_ref_" + ref_case_name(A, N, C, S))
+    return p if os.path.exists(p) else None
+
+
+def run_reference(rx: np.ndarray, pilot_asc, cp: int):
+    """Run the reference's own cpuLS.hpp code (oracle/_ref binary) on rx; None if not built."""
+    rx = np.ascontiguousarray(rx, dtype=np.complex64)
+    F, S, A, NC = rx.shape
+    N = NC - cp
+    K = N - 1
+    exe = ref_binary(A, N, cp, S)
+    if exe is None:
+        return None
+    with tempfile.TemporaryDirectory(prefix="cpuls_ref_") as d:
+        rx.tofile(os.path.join(d, "rx.bin"))
+        args = [exe, d, os.path.join(d, "rx.bin"), str(F), os.path.join(d, "out")]
+        if pilot_asc is not None:
+            np.ascontiguousarray(pilot_asc, dtype=np.complex64).tofile(os.path.join(d, "pil.bin"))
+            args.append(os.path.join(d, "pil.bin"))
+        subprocess.run(args, check=True, timeout=300, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        hconj = np.fromfile(os.path.join(d, "out.hconj"), np.complex64).reshape(F, A, K)
+        hsqrd = np.fromfile(os.path.join(d, "out.hsqrd"), np.float32).reshape(F, K)
+        comb = np.fromfile(os.path.join(d, "out.comb"), np.complex64).reshape(F, S - 1, K)
+    return {"hconj": hconj, "hsqrd": hsqrd, "combined": comb}
