@@ -1,0 +1,835 @@
+// lsmrc_capi.cu -- the only translation unit that touches CUDA: C ABI of
+// include/ofdm_lsmrc.h on top of the fused kernels in lsmrc_kernels.cuh.
+//
+// Host-side structure (B200-first, not a transliteration of gpuLS.cu):
+//  * a handle owns its streams, twiddle tables, staging and pinned result
+//    buffers once; nothing is allocated, planned or synchronised per symbol
+//    (the reference creates a cuFFT plan and cudaMallocs inside every call and
+//    calls cudaDeviceSynchronize after every launch: gpuLS.cu:377-380,452,471);
+//  * a frame batch costs two launches (pilot, data) regardless of F, S, A;
+//  * host-buffer and ring ingest are cut into lanes (stream + staging) so H2D
+//    of the next chunk overlaps the kernels and D2H of the previous ones.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ofdm_lsmrc.h"
+#include "lsmrc_kernels.cuh"
+
+using namespace lsmrc;
+
+namespace {
+
+struct PlanOps {
+    int N, P, R2, R3, teams, threads, twn, minb;
+    size_t smem;
+    void (*fill_twiddles)(float2*);
+    cudaError_t (*prepare)();
+    cudaError_t (*launch)(int mode, const KernelParams&, cudaStream_t);
+};
+
+template <class PL>
+void fill_twiddles_impl(float2* tw)
+{
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k1 = 1; k1 < PL::P; ++k1)
+        for (int t = 0; t < PL::T; ++t) {
+            const double ang = -two_pi * (double)(((long long)t * k1) % PL::N) / (double)PL::N;
+            tw[(k1 - 1) * PL::T + t] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    if (PL::R3 > 1)
+        for (int k2 = 1; k2 < PL::R2; ++k2)
+            for (int m2 = 0; m2 < PL::R3; ++m2) {
+                const double ang = -two_pi * (double)((m2 * k2) % PL::T) / (double)PL::T;
+                tw[PL::TW1 + (k2 - 1) * PL::R3 + m2] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+}
+
+template <class PL, int MINB>
+cudaError_t prepare_impl()
+{
+    cudaError_t e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_PILOT, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_DATA, MINB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
+}
+
+template <class PL, int MINB>
+cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st)
+{
+    if (mode == MODE_PILOT) {
+        lsmrc_kernel<PL, MODE_PILOT, MINB><<<p.n_frames, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+    } else {
+        const long long n_work = (long long)p.n_frames * p.n_sym_work;
+        const unsigned grid = (unsigned)((n_work + PL::TEAMS - 1) / PL::TEAMS);
+        lsmrc_kernel<PL, MODE_DATA, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <class PL, int MINB>
+PlanOps make_ops()
+{
+    PlanOps o;
+    o.N = PL::N;
+    o.P = PL::P;
+    o.R2 = PL::R2;
+    o.R3 = PL::R3;
+    o.teams = PL::TEAMS;
+    o.threads = PL::THREADS;
+    o.twn = PL::TWN;
+    o.minb = MINB;
+    o.smem = PL::SMEM_BYTES;
+    o.fill_twiddles = &fill_twiddles_impl<PL>;
+    o.prepare = &prepare_impl<PL, MINB>;
+    o.launch = &launch_impl<PL, MINB>;
+    return o;
+}
+
+// One plan per FFT size (64..4096).  N/P threads own a row; see lsmrc_kernels.cuh.
+const PlanOps* find_plan(int N)
+{
+    static const PlanOps plans[] = {
+        make_ops<Plan<64, 16, 4, 1, 32>, 4>(),
+        make_ops<Plan<128, 16, 8, 1, 16>, 4>(),
+        make_ops<Plan<256, 16, 16, 1, 8>, 4>(),
+        make_ops<Plan<512, 32, 16, 1, 8>, 3>(),
+        make_ops<Plan<1024, 32, 32, 1, 4>, 3>(),
+        make_ops<Plan<2048, 32, 16, 4, 2>, 3>(),
+        make_ops<Plan<4096, 32, 32, 4, 1>, 3>(),
+    };
+    for (const PlanOps& o : plans)
+        if (o.N == N) return &o;
+    return nullptr;
+}
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    float2* d_rx = nullptr;     // [max_frames][S][A][N+C]
+    float2* d_hconj = nullptr;  // [max_frames][A][K]
+    float* d_hsqrd = nullptr;   // [max_frames][K]
+    float2* d_comb = nullptr;   // [max_frames][S-1][K]
+    uint8_t* d_bits = nullptr;  // [max_frames][S-1][row]
+    // pinned single-frame result buffers of the ring path
+    float2* h_comb = nullptr;
+    uint8_t* h_bits = nullptr;
+    float2* h_hconj = nullptr;
+    bool busy = false;
+};
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+}  // namespace
+
+struct lsmrc_ctx {
+    lsmrc_config cfg;
+    int K = 0;
+    size_t row_bytes = 0;
+    size_t slot_elems = 0;   // A*(N+C)
+    size_t frame_elems = 0;  // S*slot
+    const PlanOps* ops = nullptr;
+    float2* d_tw = nullptr;
+    float2* d_pilot_bin = nullptr;
+    bool have_pilot = false;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    // scratch channel state of the device-resident path when the caller passes NULL
+    float2* d_scr_hconj = nullptr;
+    float* d_scr_hsqrd = nullptr;
+    int scr_frames = 0;
+    // per-symbol path state (one frame)
+    float2* d_sym = nullptr;
+    float2* d_one_hconj = nullptr;
+    float* d_one_hsqrd = nullptr;
+    float2* d_one_comb = nullptr;
+    uint8_t* d_one_bits = nullptr;
+    float2* h_one_sym = nullptr;   // pinned staging for pageable ring slots
+    float2* h_one_comb = nullptr;  // pinned
+    uint8_t* h_one_bits = nullptr;
+    bool have_channel = false;
+    std::vector<Lane> lanes;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool ev_valid = false;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(lsmrc_ctx* h, int code, const std::string& msg)
+{
+    if (h) h->err = msg;
+    else {
+        std::lock_guard<std::mutex> g(g_err_mutex);
+        g_create_error = msg;
+    }
+    return code;
+}
+
+int fail_cuda(lsmrc_ctx* h, cudaError_t e, const char* what)
+{
+    return fail(h, LSMRC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(h, expr)                                                  \
+    do {                                                             \
+        cudaError_t _e = (expr);                                     \
+        if (_e != cudaSuccess) return fail_cuda((h), _e, #expr);     \
+    } while (0)
+
+cudaStream_t compute_stream(lsmrc_ctx* h) { return h->use_user_stream ? h->user_stream : h->own_stream; }
+
+KernelParams base_params(lsmrc_ctx* h)
+{
+    KernelParams p;
+    std::memset(&p, 0, sizeof(p));
+    const lsmrc_config& c = h->cfg;
+    p.sym_stride = (long long)h->slot_elems;
+    p.frame_stride = (long long)h->frame_elems;
+    p.ant_stride = c.fft_size + c.cp_len;
+    p.cp = c.cp_len;
+    p.n_ant = c.n_ant;
+    p.qam_bits = c.qam_bits;
+    p.pilot_bin = h->d_pilot_bin;
+    p.bits_row_bytes = (int)h->row_bytes;
+    p.twiddles = h->d_tw;
+    return p;
+}
+
+// pilot + data launches for n_frames whole frames
+int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frames, float2* d_hconj,
+                  float* d_hsqrd, float2* d_comb, uint8_t* d_bits, bool timed)
+{
+    KernelParams p = base_params(h);
+    p.rx = d_rx;
+    p.n_frames = n_frames;
+    p.hconj = d_hconj;
+    p.hsqrd = d_hsqrd;
+    p.combined = d_comb;
+    p.bits = d_bits;
+    if (timed) CK(h, cudaEventRecord(h->ev0, st));
+    p.first_sym = 0;
+    p.n_sym_work = 1;
+    CK(h, h->ops->launch(MODE_PILOT, p, st));
+    h->launches++;
+    if (timed) CK(h, cudaEventRecord(h->ev1, st));
+    if (h->cfg.n_sym > 1) {
+        p.first_sym = 1;
+        p.n_sym_work = h->cfg.n_sym - 1;
+        CK(h, h->ops->launch(MODE_DATA, p, st));
+        h->launches++;
+    }
+    if (timed) {
+        CK(h, cudaEventRecord(h->ev2, st));
+        h->ev_valid = true;
+    }
+    return LSMRC_OK;
+}
+
+bool is_pinned_or_device(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+struct ScopedPin {
+    void* p = nullptr;
+    bool pinned = false;
+    void pin(const void* ptr, size_t bytes)
+    {
+        if (!ptr || bytes == 0 || is_pinned_or_device(ptr)) return;
+        if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+            p = const_cast<void*>(ptr);
+            pinned = true;
+        } else {
+            cudaGetLastError();  // fall back to staged (synchronous) copies
+        }
+    }
+    ~ScopedPin()
+    {
+        if (pinned) cudaHostUnregister(p);
+    }
+};
+
+int alloc_lane(lsmrc_ctx* h, Lane& L)
+{
+    const lsmrc_config& c = h->cfg;
+    const size_t F = (size_t)c.max_frames;
+    const size_t nd = (size_t)(c.n_sym > 1 ? c.n_sym - 1 : 1);
+    CK(h, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    CK(h, cudaEventCreateWithFlags(&L.copied, cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    CK(h, cudaMalloc(&L.d_rx, F * h->frame_elems * sizeof(float2)));
+    CK(h, cudaMalloc(&L.d_hconj, F * (size_t)c.n_ant * h->K * sizeof(float2)));
+    CK(h, cudaMalloc(&L.d_hsqrd, F * (size_t)h->K * sizeof(float)));
+    CK(h, cudaMalloc(&L.d_comb, F * nd * h->K * sizeof(float2)));
+    CK(h, cudaMalloc(&L.d_bits, F * nd * h->row_bytes));
+    CK(h, cudaMallocHost(&L.h_comb, nd * h->K * sizeof(float2)));
+    CK(h, cudaMallocHost(&L.h_bits, nd * h->row_bytes));
+    CK(h, cudaMallocHost(&L.h_hconj, (size_t)c.n_ant * h->K * sizeof(float2)));
+    return LSMRC_OK;
+}
+
+void free_lane(Lane& L)
+{
+    if (L.st) cudaStreamSynchronize(L.st);
+    cudaFree(L.d_rx);
+    cudaFree(L.d_hconj);
+    cudaFree(L.d_hsqrd);
+    cudaFree(L.d_comb);
+    cudaFree(L.d_bits);
+    cudaFreeHost(L.h_comb);
+    cudaFreeHost(L.h_bits);
+    cudaFreeHost(L.h_hconj);
+    if (L.copied) cudaEventDestroy(L.copied);
+    if (L.done) cudaEventDestroy(L.done);
+    if (L.st) cudaStreamDestroy(L.st);
+    L = Lane();
+}
+
+int ensure_lanes(lsmrc_ctx* h)
+{
+    if (!h->lanes.empty()) return LSMRC_OK;
+    h->lanes.resize((size_t)h->cfg.n_lanes);
+    for (Lane& L : h->lanes) {
+        int rc = alloc_lane(h, L);
+        if (rc != LSMRC_OK) {
+            for (Lane& M : h->lanes) free_lane(M);
+            h->lanes.clear();
+            return rc;
+        }
+    }
+    return LSMRC_OK;
+}
+
+int ensure_symbol_state(lsmrc_ctx* h)
+{
+    if (h->d_sym) return LSMRC_OK;
+    const lsmrc_config& c = h->cfg;
+    CK(h, cudaMalloc(&h->d_sym, h->slot_elems * sizeof(float2)));
+    CK(h, cudaMalloc(&h->d_one_hconj, (size_t)c.n_ant * h->K * sizeof(float2)));
+    CK(h, cudaMalloc(&h->d_one_hsqrd, (size_t)h->K * sizeof(float)));
+    CK(h, cudaMalloc(&h->d_one_comb, (size_t)h->K * sizeof(float2)));
+    CK(h, cudaMalloc(&h->d_one_bits, h->row_bytes));
+    CK(h, cudaMallocHost(&h->h_one_sym, h->slot_elems * sizeof(float2)));
+    CK(h, cudaMallocHost(&h->h_one_comb, (size_t)h->K * sizeof(float2)));
+    CK(h, cudaMallocHost(&h->h_one_bits, h->row_bytes));
+    return LSMRC_OK;
+}
+
+// stage one ring slot onto the device (the reference copies straight from pageable shm,
+// ShMemSymBuff_gpu.hpp:386-387, which makes cudaMemcpyAsync synchronous)
+int stage_symbol(lsmrc_ctx* h, const void* rx_sym, int on_device, const float2** d_out)
+{
+    if (on_device) {
+        *d_out = static_cast<const float2*>(rx_sym);
+        return LSMRC_OK;
+    }
+    const size_t bytes = h->slot_elems * sizeof(float2);
+    cudaStream_t st = h->own_stream;
+    const void* src = rx_sym;
+    if (!is_pinned_or_device(rx_sym)) {
+        CK(h, cudaStreamSynchronize(st));  // staging buffer may still be in flight
+        std::memcpy(h->h_one_sym, rx_sym, bytes);
+        src = h->h_one_sym;
+    }
+    CK(h, cudaMemcpyAsync(h->d_sym, src, bytes, cudaMemcpyHostToDevice, st));
+    *d_out = h->d_sym;
+    return LSMRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsmrc_abi_version(void) { return LSMRC_ABI_VERSION; }
+
+const char* lsmrc_error_name(int code)
+{
+    switch (code) {
+        case LSMRC_OK: return "LSMRC_OK";
+        case LSMRC_ERR_INVALID: return "LSMRC_ERR_INVALID";
+        case LSMRC_ERR_CUDA: return "LSMRC_ERR_CUDA";
+        case LSMRC_ERR_UNSUPPORTED: return "LSMRC_ERR_UNSUPPORTED";
+        case LSMRC_ERR_NO_PILOT: return "LSMRC_ERR_NO_PILOT";
+        case LSMRC_ERR_NO_DEVICE: return "LSMRC_ERR_NO_DEVICE";
+        case LSMRC_ERR_STATE: return "LSMRC_ERR_STATE";
+        default: return "LSMRC_ERR_UNKNOWN";
+    }
+}
+
+const char* lsmrc_last_error(lsmrc_handle h)
+{
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+size_t lsmrc_bits_row_bytes(int fft_size, int qam_bits)
+{
+    if (fft_size < 2 || qam_bits < 1) return 0;
+    return ((size_t)(fft_size - 1) * (size_t)qam_bits + 7u) / 8u;
+}
+
+size_t lsmrc_rx_frame_elems(const lsmrc_config* c)
+{
+    if (!c) return 0;
+    return (size_t)c->n_sym * (size_t)c->n_ant * (size_t)(c->fft_size + c->cp_len);
+}
+
+int lsmrc_supported_fft_size(int fft_size) { return find_plan(fft_size) != nullptr; }
+
+int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
+{
+    if (!cfg || !out) return fail(nullptr, LSMRC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->n_ant < 1 || cfg->n_sym < 1 || cfg->cp_len < 0 || cfg->max_frames < 1 || cfg->n_lanes < 1 ||
+        cfg->n_lanes > 64)
+        return fail(nullptr, LSMRC_ERR_INVALID, "n_ant/n_sym/max_frames/n_lanes must be >= 1, cp_len >= 0");
+    if (cfg->qam_bits != 2 && cfg->qam_bits != 4 && cfg->qam_bits != 6)
+        return fail(nullptr, LSMRC_ERR_UNSUPPORTED, "qam_bits must be 2, 4 or 6");
+    const PlanOps* ops = find_plan(cfg->fft_size);
+    if (!ops) return fail(nullptr, LSMRC_ERR_UNSUPPORTED, "fft_size must be a power of two in 64..4096");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LSMRC_ERR_NO_DEVICE,
+                    std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LSMRC_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail_cuda(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, LSMRC_ERR_NO_DEVICE,
+                    std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "); this library is built for sm_100a only");
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail_cuda(nullptr, e, "cudaSetDevice");
+
+    lsmrc_ctx* h = new lsmrc_ctx();
+    h->cfg = *cfg;
+    h->K = cfg->fft_size - 1;
+    h->row_bytes = lsmrc_bits_row_bytes(cfg->fft_size, cfg->qam_bits);
+    h->slot_elems = (size_t)cfg->n_ant * (size_t)(cfg->fft_size + cfg->cp_len);
+    h->frame_elems = (size_t)cfg->n_sym * h->slot_elems;
+    h->ops = ops;
+
+    auto bail = [&](int rc) {
+        std::string msg = h->err;
+        lsmrc_destroy(h);
+        return fail(nullptr, rc, msg);
+    };
+    if ((e = ops->prepare()) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute"); return bail(LSMRC_ERR_CUDA); }
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(h, e, "cudaStreamCreate"); return bail(LSMRC_ERR_CUDA); }
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev2)) != cudaSuccess) { fail_cuda(h, e, "cudaEventCreate"); return bail(LSMRC_ERR_CUDA); }
+    std::vector<float2> tw((size_t)ops->twn);
+    ops->fill_twiddles(tw.data());
+    if ((e = cudaMalloc(&h->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc twiddles"); return bail(LSMRC_ERR_CUDA); }
+    if ((e = cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { fail_cuda(h, e, "cudaMemcpy twiddles"); return bail(LSMRC_ERR_CUDA); }
+    if ((e = cudaMalloc(&h->d_pilot_bin, (size_t)h->K * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc pilot"); return bail(LSMRC_ERR_CUDA); }
+    *out = h;
+    return LSMRC_OK;
+}
+
+int lsmrc_destroy(lsmrc_handle h)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (Lane& L : h->lanes) free_lane(L);
+    cudaFree(h->d_tw);
+    cudaFree(h->d_pilot_bin);
+    cudaFree(h->d_scr_hconj);
+    cudaFree(h->d_scr_hsqrd);
+    cudaFree(h->d_sym);
+    cudaFree(h->d_one_hconj);
+    cudaFree(h->d_one_hsqrd);
+    cudaFree(h->d_one_comb);
+    cudaFree(h->d_one_bits);
+    cudaFreeHost(h->h_one_sym);
+    cudaFreeHost(h->h_one_comb);
+    cudaFreeHost(h->h_one_bits);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaGetLastError();
+    delete h;
+    return LSMRC_OK;
+}
+
+int lsmrc_set_pilot(lsmrc_handle h, const float* pilot_asc, int K)
+{
+    if (!h || !pilot_asc) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (K != h->K) return fail(h, LSMRC_ERR_INVALID, "pilot length must be fft_size-1");
+    CK(h, cudaSetDevice(h->cfg.device));
+    // Pilots.dat is ascending frequency; the kernels index by FFT bin.  Same roll as
+    // matrix_readX (cpuLS.hpp:105-112): X_bin[k] = P[(k + (K+1)/2) mod K].
+    std::vector<float2> xb((size_t)K);
+    const float2* P = reinterpret_cast<const float2*>(pilot_asc);
+    for (int k = 0; k < K; ++k) {
+        xb[(size_t)k] = P[(k + (K + 1) / 2) % K];
+        if (xb[(size_t)k].x == 0.f && xb[(size_t)k].y == 0.f) return fail(h, LSMRC_ERR_INVALID, "pilot contains a zero subcarrier");
+    }
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    CK(h, cudaMemcpy(h->d_pilot_bin, xb.data(), (size_t)K * sizeof(float2), cudaMemcpyHostToDevice));
+    h->have_pilot = true;
+    return LSMRC_OK;
+}
+
+int lsmrc_set_pilot_file(lsmrc_handle h, const char* path)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    std::vector<float2> p((size_t)h->K);
+    int used_fallback = 0;
+    FILE* f = path ? std::fopen(path, "rb") : nullptr;
+    if (!f) {
+        // CPU-reference fallback (cpuLS.hpp:85-88).  The GPU reference uses 1+1i instead
+        // (gpuLS.cu:58-62); the two disagree, we follow the CPU path we are checked against.
+        for (float2& v : p) v = make_float2(0.707f, 0.707f);
+        used_fallback = 1;
+    } else {
+        const size_t got = std::fread(p.data(), sizeof(float2), p.size(), f);
+        std::fclose(f);
+        if (got != p.size()) return fail(h, LSMRC_ERR_INVALID, "pilot file shorter than K complex64 values");
+    }
+    const int rc = lsmrc_set_pilot(h, reinterpret_cast<const float*>(p.data()), h->K);
+    return rc == LSMRC_OK ? used_fallback : rc;
+}
+
+int lsmrc_demod_frames_device(lsmrc_handle h, const void* d_rx, int n_frames, void* d_hconj, void* d_hsqrd,
+                              void* d_combined, void* d_bits)
+{
+    if (!h || !d_rx || !d_combined) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_frames < 0) return fail(h, LSMRC_ERR_INVALID, "n_frames < 0");
+    if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
+    if (n_frames == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    if ((!d_hconj || !d_hsqrd) && h->scr_frames < n_frames) {
+        CK(h, cudaStreamSynchronize(compute_stream(h)));
+        cudaFree(h->d_scr_hconj);
+        cudaFree(h->d_scr_hsqrd);
+        h->d_scr_hconj = nullptr;
+        h->d_scr_hsqrd = nullptr;
+        h->scr_frames = 0;
+        CK(h, cudaMalloc(&h->d_scr_hconj, (size_t)n_frames * h->cfg.n_ant * h->K * sizeof(float2)));
+        CK(h, cudaMalloc(&h->d_scr_hsqrd, (size_t)n_frames * h->K * sizeof(float)));
+        h->scr_frames = n_frames;
+    }
+    float2* hc = d_hconj ? static_cast<float2*>(d_hconj) : h->d_scr_hconj;
+    float* hs = d_hsqrd ? static_cast<float*>(d_hsqrd) : h->d_scr_hsqrd;
+    return launch_frames(h, compute_stream(h), static_cast<const float2*>(d_rx), n_frames, hc, hs,
+                         static_cast<float2*>(d_combined), static_cast<uint8_t*>(d_bits), h->timing);
+}
+
+int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,
+                            void* h_combined, void* h_bits)
+{
+    if (!h || !h_rx || !h_combined) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_frames < 0) return fail(h, LSMRC_ERR_INVALID, "n_frames < 0");
+    if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
+    if (n_frames == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lanes(h);
+    if (rc != LSMRC_OK) return rc;
+    const lsmrc_config& c = h->cfg;
+    const size_t nd = (size_t)(c.n_sym - 1);
+    const size_t rx_fb = h->frame_elems * sizeof(float2);
+    const size_t hc_fb = (size_t)c.n_ant * h->K * sizeof(float2);
+    const size_t hs_fb = (size_t)h->K * sizeof(float);
+    const size_t cb_fb = nd * h->K * sizeof(float2);
+    const size_t bt_fb = nd * h->row_bytes;
+    ScopedPin pin_rx, pin_hc, pin_hs, pin_cb, pin_bt;
+    pin_rx.pin(h_rx, rx_fb * n_frames);
+    pin_hc.pin(h_hconj, hc_fb * n_frames);
+    pin_hs.pin(h_hsqrd, hs_fb * n_frames);
+    pin_cb.pin(h_combined, cb_fb * n_frames);
+    pin_bt.pin(h_bits, bt_fb * n_frames);
+
+    int chunk_idx = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += c.max_frames, ++chunk_idx) {
+        const int nf = (n_frames - f0 < c.max_frames) ? (n_frames - f0) : c.max_frames;
+        Lane& L = h->lanes[(size_t)chunk_idx % h->lanes.size()];
+        const char* src = static_cast<const char*>(h_rx) + (size_t)f0 * rx_fb;
+        CK(h, cudaMemcpyAsync(L.d_rx, src, rx_fb * nf, cudaMemcpyHostToDevice, L.st));
+        rc = launch_frames(h, L.st, L.d_rx, nf, L.d_hconj, L.d_hsqrd, L.d_comb, h_bits ? L.d_bits : nullptr, false);
+        if (rc != LSMRC_OK) return rc;
+        if (nd > 0)
+            CK(h, cudaMemcpyAsync(static_cast<char*>(h_combined) + (size_t)f0 * cb_fb, L.d_comb, cb_fb * nf,
+                                  cudaMemcpyDeviceToHost, L.st));
+        if (h_bits && nd > 0)
+            CK(h, cudaMemcpyAsync(static_cast<char*>(h_bits) + (size_t)f0 * bt_fb, L.d_bits, bt_fb * nf,
+                                  cudaMemcpyDeviceToHost, L.st));
+        if (h_hconj)
+            CK(h, cudaMemcpyAsync(static_cast<char*>(h_hconj) + (size_t)f0 * hc_fb, L.d_hconj, hc_fb * nf,
+                                  cudaMemcpyDeviceToHost, L.st));
+        if (h_hsqrd)
+            CK(h, cudaMemcpyAsync(static_cast<char*>(h_hsqrd) + (size_t)f0 * hs_fb, L.d_hsqrd, hs_fb * nf,
+                                  cudaMemcpyDeviceToHost, L.st));
+    }
+    for (Lane& L : h->lanes) CK(h, cudaStreamSynchronize(L.st));
+    return LSMRC_OK;
+}
+
+int lsmrc_first_vector(lsmrc_handle h, const void* rx_sym, int on_device)
+{
+    if (!h || !rx_sym) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_symbol_state(h);
+    if (rc != LSMRC_OK) return rc;
+    const float2* d_in = nullptr;
+    if ((rc = stage_symbol(h, rx_sym, on_device, &d_in)) != LSMRC_OK) return rc;
+    KernelParams p = base_params(h);
+    p.rx = d_in;
+    p.frame_stride = 0;
+    p.sym_stride = 0;
+    p.first_sym = 0;
+    p.n_sym_work = 1;
+    p.n_frames = 1;
+    p.hconj = h->d_one_hconj;
+    p.hsqrd = h->d_one_hsqrd;
+    CK(h, h->ops->launch(MODE_PILOT, p, h->own_stream));
+    h->launches++;
+    h->have_channel = true;
+    return LSMRC_OK;
+}
+
+int lsmrc_demod_one_symbol(lsmrc_handle h, const void* rx_sym, int on_device, void* h_combined, void* h_bits)
+{
+    if (!h || !rx_sym || !h_combined) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (!h->have_channel) return fail(h, LSMRC_ERR_STATE, "lsmrc_first_vector must run before lsmrc_demod_one_symbol");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const float2* d_in = nullptr;
+    int rc = stage_symbol(h, rx_sym, on_device, &d_in);
+    if (rc != LSMRC_OK) return rc;
+    KernelParams p = base_params(h);
+    p.rx = d_in;
+    p.frame_stride = 0;
+    p.sym_stride = 0;
+    p.first_sym = 0;
+    p.n_sym_work = 1;
+    p.n_frames = 1;
+    p.hconj = h->d_one_hconj;
+    p.hsqrd = h->d_one_hsqrd;
+    p.combined = h->d_one_comb;
+    p.bits = h->d_one_bits;
+    cudaStream_t st = h->own_stream;
+    CK(h, h->ops->launch(MODE_DATA, p, st));
+    h->launches++;
+    CK(h, cudaMemcpyAsync(h->h_one_comb, h->d_one_comb, (size_t)h->K * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    if (h_bits) CK(h, cudaMemcpyAsync(h->h_one_bits, h->d_one_bits, h->row_bytes, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    std::memcpy(h_combined, h->h_one_comb, (size_t)h->K * sizeof(float2));
+    if (h_bits) std::memcpy(h_bits, h->h_one_bits, h->row_bytes);
+    return LSMRC_OK;
+}
+
+int lsmrc_get_channel(lsmrc_handle h, void* h_hconj, void* h_hsqrd)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    if (!h->have_channel) return fail(h, LSMRC_ERR_STATE, "no channel estimate yet");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    if (h_hconj) CK(h, cudaMemcpy(h_hconj, h->d_one_hconj, (size_t)h->cfg.n_ant * h->K * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (h_hsqrd) CK(h, cudaMemcpy(h_hsqrd, h->d_one_hsqrd, (size_t)h->K * sizeof(float), cudaMemcpyDeviceToHost));
+    return LSMRC_OK;
+}
+
+// ---- ring lanes -----------------------------------------------------------------------
+
+static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L)
+{
+    const lsmrc_config& c = h->cfg;
+    const size_t nd = (size_t)(c.n_sym - 1);
+    CK(h, cudaEventRecord(L.copied, L.st));
+    int rc = launch_frames(h, L.st, L.d_rx, 1, L.d_hconj, L.d_hsqrd, L.d_comb, L.d_bits, false);
+    if (rc != LSMRC_OK) return rc;
+    if (nd > 0) {
+        CK(h, cudaMemcpyAsync(L.h_comb, L.d_comb, nd * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
+        CK(h, cudaMemcpyAsync(L.h_bits, L.d_bits, nd * h->row_bytes, cudaMemcpyDeviceToHost, L.st));
+    }
+    CK(h, cudaMemcpyAsync(L.h_hconj, L.d_hconj, (size_t)c.n_ant * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
+    CK(h, cudaEventRecord(L.done, L.st));
+    L.busy = true;
+    return LSMRC_OK;
+}
+
+int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_t slot_stride_bytes)
+{
+    if (!h || !h_slots) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
+    if (lane < 0 || lane >= h->cfg.n_lanes) return fail(h, LSMRC_ERR_INVALID, "lane out of range");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lanes(h);
+    if (rc != LSMRC_OK) return rc;
+    Lane& L = h->lanes[(size_t)lane];
+    const size_t slot_bytes = h->slot_elems * sizeof(float2);
+    if (slot_stride_bytes == slot_bytes) {
+        CK(h, cudaMemcpyAsync(L.d_rx, h_slots, slot_bytes * h->cfg.n_sym, cudaMemcpyHostToDevice, L.st));
+    } else {
+        if (slot_stride_bytes < slot_bytes) return fail(h, LSMRC_ERR_INVALID, "slot stride smaller than a slot");
+        CK(h, cudaMemcpy2DAsync(L.d_rx, slot_bytes, h_slots, slot_stride_bytes, slot_bytes, (size_t)h->cfg.n_sym,
+                                cudaMemcpyHostToDevice, L.st));
+    }
+    return ring_enqueue_compute(h, L);
+}
+
+int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void* h_first, int n_first, const void* h_second)
+{
+    if (!h || !h_first) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
+    if (lane < 0 || lane >= h->cfg.n_lanes) return fail(h, LSMRC_ERR_INVALID, "lane out of range");
+    if (n_first < 0 || n_first > h->cfg.n_sym || (n_first < h->cfg.n_sym && !h_second))
+        return fail(h, LSMRC_ERR_INVALID, "bad split");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_lanes(h);
+    if (rc != LSMRC_OK) return rc;
+    Lane& L = h->lanes[(size_t)lane];
+    const size_t slot_bytes = h->slot_elems * sizeof(float2);
+    if (n_first > 0) CK(h, cudaMemcpyAsync(L.d_rx, h_first, slot_bytes * n_first, cudaMemcpyHostToDevice, L.st));
+    if (n_first < h->cfg.n_sym)
+        CK(h, cudaMemcpyAsync(reinterpret_cast<char*>(L.d_rx) + slot_bytes * n_first, h_second,
+                              slot_bytes * (h->cfg.n_sym - n_first), cudaMemcpyHostToDevice, L.st));
+    return ring_enqueue_compute(h, L);
+}
+
+int lsmrc_ring_copy_done(lsmrc_handle h, int lane)
+{
+    if (!h || lane < 0 || lane >= (int)h->lanes.size()) return fail(h, LSMRC_ERR_INVALID, "lane out of range");
+    CK(h, cudaEventSynchronize(h->lanes[(size_t)lane].copied));
+    return LSMRC_OK;
+}
+
+int lsmrc_ring_wait(lsmrc_handle h, int lane, const void** combined, const void** bits, const void** hconj)
+{
+    if (!h || lane < 0 || lane >= (int)h->lanes.size()) return fail(h, LSMRC_ERR_INVALID, "lane out of range");
+    Lane& L = h->lanes[(size_t)lane];
+    if (!L.busy) return fail(h, LSMRC_ERR_STATE, "lane has nothing in flight");
+    CK(h, cudaEventSynchronize(L.done));
+    L.busy = false;
+    if (combined) *combined = L.h_comb;
+    if (bits) *bits = L.h_bits;
+    if (hconj) *hconj = L.h_hconj;
+    return LSMRC_OK;
+}
+
+// ---- plumbing ---------------------------------------------------------------------------
+
+int lsmrc_dev_alloc(lsmrc_handle h, size_t bytes, void** d_ptr)
+{
+    if (!h || !d_ptr) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMalloc(d_ptr, bytes));
+    return LSMRC_OK;
+}
+int lsmrc_dev_free(lsmrc_handle h, void* d_ptr)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaFree(d_ptr));
+    return LSMRC_OK;
+}
+int lsmrc_copy_to_device(lsmrc_handle h, void* d_dst, const void* h_src, size_t bytes)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return LSMRC_OK;
+}
+int lsmrc_copy_to_host(lsmrc_handle h, void* h_dst, const void* d_src, size_t bytes)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(compute_stream(h)));
+    CK(h, cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return LSMRC_OK;
+}
+int lsmrc_host_alloc(lsmrc_handle h, size_t bytes, void** h_ptr)
+{
+    if (!h || !h_ptr) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMallocHost(h_ptr, bytes));
+    return LSMRC_OK;
+}
+int lsmrc_host_free(lsmrc_handle h, void* h_ptr)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaFreeHost(h_ptr));
+    return LSMRC_OK;
+}
+int lsmrc_host_register(lsmrc_handle h, void* h_ptr, size_t bytes)
+{
+    if (!h || !h_ptr) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault));
+    return LSMRC_OK;
+}
+int lsmrc_host_unregister(lsmrc_handle h, void* h_ptr)
+{
+    if (!h || !h_ptr) return LSMRC_ERR_INVALID;
+    CK(h, cudaHostUnregister(h_ptr));
+    return LSMRC_OK;
+}
+int lsmrc_set_stream(lsmrc_handle h, void* cuda_stream)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    h->user_stream = static_cast<cudaStream_t>(cuda_stream);
+    h->use_user_stream = true;
+    return LSMRC_OK;
+}
+int lsmrc_sync(lsmrc_handle h)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(compute_stream(h)));
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    for (Lane& L : h->lanes) CK(h, cudaStreamSynchronize(L.st));
+    return LSMRC_OK;
+}
+int lsmrc_set_timing(lsmrc_handle h, int enabled)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    h->timing = enabled != 0;
+    return LSMRC_OK;
+}
+int lsmrc_last_kernel_ms(lsmrc_handle h, float* pilot_ms, float* data_ms)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    if (!h->ev_valid) return fail(h, LSMRC_ERR_STATE, "no timed call yet (lsmrc_set_timing)");
+    CK(h, cudaEventSynchronize(h->ev2));
+    float a = 0.f, b = 0.f;
+    CK(h, cudaEventElapsedTime(&a, h->ev0, h->ev1));
+    CK(h, cudaEventElapsedTime(&b, h->ev1, h->ev2));
+    if (pilot_ms) *pilot_ms = a;
+    if (data_ms) *data_ms = b;
+    return LSMRC_OK;
+}
+long long lsmrc_launch_count(lsmrc_handle h) { return h ? h->launches : 0; }
+int lsmrc_describe_plan(lsmrc_handle h, char* buf, size_t buf_len)
+{
+    if (!h || !buf || buf_len == 0) return LSMRC_ERR_INVALID;
+    const PlanOps* o = h->ops;
+    std::snprintf(buf, buf_len, "N=%d P=%d R2=%d R3=%d teams=%d threads=%d smem=%zu minblocks=%d", o->N, o->P, o->R2,
+                  o->R3, o->teams, o->threads, o->smem, o->minb);
+    return LSMRC_OK;
+}
+
+}  // extern "C"

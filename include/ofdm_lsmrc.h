@@ -1,0 +1,153 @@
+/*
+ * ofdm_lsmrc.h -- C ABI of the B200-native uplink OFDM receiver hot path
+ * (CP strip -> per-antenna FFT -> LS channel estimate -> MRC -> hard QAM demap).
+ *
+ * This is the drop-in boundary for the reference's GPU path: the reference has no
+ * FFI layer, its surface is `class gpuLS` (gpuLS.cuh:72-113) driven by
+ * gpuLS_main.cu:66-141 plus the ShMemSymBuff ring.  Every entry point below names
+ * the reference interface it replaces.  Plain pointers and sizes only; no CUDA,
+ * torch or C++ types cross this boundary, so the C++ facade in
+ * gpu-accel-ofdm-ls-mrc_b200/host/ (same class and method names as the reference)
+ * and any other binding (ctypes, cgo, JNI ...) can sit on top of it.
+ *
+ * Dimensions are runtime here; the reference fixes them with -D macros
+ * (ShMemSymBuff.hpp:42-67): A = numOfRows, N = dimension, C = prefix,
+ * S = lenOfBuffer (symbol 0 of a frame is the pilot), K = N-1 used subcarriers.
+ *
+ * Data layouts (all complex64 = interleaved float re,im -- complexF /
+ * cuFloatComplex, ShMemSymBuff.hpp:86-89):
+ *   rx        [F][S][A][N+C]  antenna-samples exactly as the ring slots hold them
+ *                             (struct symbol, ShMemSymBuff.hpp:92-94), CP included
+ *   pilot     [K]             ascending frequency, the Pilots.dat order (cpuLS.hpp:93)
+ *   hconj     [F][A][K]       conj(H), FFT-bin order (bin k+1 at index k) -- what the
+ *                             reference keeps in dH/Hconj (gpuLS.cu:158-182)
+ *   hsqrd     [F][K]          sum_a |H|^2 (float)      (gpuLS.cu:185-209)
+ *   combined  [F][S-1][K]     MRC output, ascending frequency -- the Output_gpu.dat
+ *                             record order (gpuLS_main.cu:114-126)
+ *   bits      [F][S-1][row]   hard-demapped bits, LSB first, symbol i at stream bits
+ *                             [i*b, i*b+b) of its row; row = lsmrc_bits_row_bytes()
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * LSMRC_ERR_NO_DEVICE / LSMRC_ERR_CUDA when no sm_100 GPU is usable.
+ * Error convention: 0 on success, negative LSMRC_ERR_* otherwise (the reference
+ * ignores every CUDA status and returns void); lsmrc_last_error() gives text.
+ */
+#ifndef OFDM_LSMRC_H
+#define OFDM_LSMRC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSMRC_ABI_VERSION 1
+
+enum {
+    LSMRC_OK = 0,
+    LSMRC_ERR_INVALID = -1,     /* bad argument / dimension */
+    LSMRC_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    LSMRC_ERR_UNSUPPORTED = -3, /* FFT size or QAM order not built */
+    LSMRC_ERR_NO_PILOT = -4,    /* lsmrc_set_pilot* not called yet */
+    LSMRC_ERR_NO_DEVICE = -5,   /* no CUDA device / not sm_100 */
+    LSMRC_ERR_STATE = -6        /* call order (e.g. data symbol before pilot symbol) */
+};
+
+typedef struct lsmrc_ctx *lsmrc_handle;
+
+typedef struct lsmrc_config {
+    int n_ant;      /* A: numOfRows   (ShMemSymBuff.hpp:42-44) */
+    int fft_size;   /* N: dimension   (ShMemSymBuff.hpp:46-48), power of two 64..4096 */
+    int cp_len;     /* C: prefix      (ShMemSymBuff.hpp:50-52) */
+    int n_sym;      /* S: lenOfBuffer (ShMemSymBuff.hpp:63-65), pilot + S-1 data symbols */
+    int qam_bits;   /* 2 (QPSK), 4 (16-QAM), 6 (64-QAM) */
+    int max_frames; /* frames per chunk of the host-buffer path (device staging capacity) */
+    int device;     /* CUDA ordinal; the reference hard-codes 0 (gpuLS_main.cu:69) */
+    int n_lanes;    /* copy/compute lanes (streams) of the host-buffer and ring paths, >= 1 */
+} lsmrc_config;
+
+/* ---- lifetime (replaces gpuLS::gpuLS(), gpuLS.cu:43-47, and the cudaMalloc block of
+ *      gpuLS_main.cu:73-91) ------------------------------------------------------- */
+int lsmrc_abi_version(void);
+int lsmrc_create(const lsmrc_config *cfg, lsmrc_handle *out);
+int lsmrc_destroy(lsmrc_handle h);
+const char *lsmrc_last_error(lsmrc_handle h); /* h may be NULL: last create() failure */
+const char *lsmrc_error_name(int code);
+
+/* ---- geometry helpers -------------------------------------------------------------- */
+size_t lsmrc_bits_row_bytes(int fft_size, int qam_bits);         /* ceil((N-1)*b/8) */
+size_t lsmrc_rx_frame_elems(const lsmrc_config *cfg);            /* S*A*(N+C) complex */
+int lsmrc_supported_fft_size(int fft_size);                      /* 1 if a plan is built */
+
+/* ---- pilot (replaces gpuLS::matrix_readX, gpuLS.cu:53-86, and copyPilotToGPU :88-106) - */
+/* pilot_asc: K complex64 in ascending-frequency (file) order; rolled to bin order inside. */
+int lsmrc_set_pilot(lsmrc_handle h, const float *pilot_asc, int K);
+/* Reads K complex64 from `path` (Pilots.dat format).  When the file cannot be opened the
+ * CPU reference's fallback 0.707+0.707i is used (cpuLS.hpp:85-88) and 1 is returned. */
+int lsmrc_set_pilot_file(lsmrc_handle h, const char *path);
+
+/* ---- whole frames, device-resident (replaces gpuLS::demodOneFrameCUDA gpuLS.cu:575 /
+ *      demodOptimized :677 / demodCuBlas :771).  All pointers are DEVICE pointers.
+ *      d_hconj / d_hsqrd / d_bits may be NULL (internal scratch / skipped).  The work is
+ *      enqueued on the handle's compute stream; call lsmrc_sync() before reading. ------ */
+int lsmrc_demod_frames_device(lsmrc_handle h, const void *d_rx, int n_frames, void *d_hconj,
+                              void *d_hsqrd, void *d_combined, void *d_bits);
+
+/* ---- whole frames, host buffers (replaces gpuLS::demodOneFrame gpuLS.cu:475: H2D,
+ *      compute, D2H inside).  Frames are cut into chunks of <= max_frames and pipelined
+ *      over n_lanes streams so that H2D(i+1), kernels(i) and D2H(i-1) overlap.  Host
+ *      buffers that are not pinned are pinned for the duration of the call.
+ *      h_hconj / h_hsqrd / h_bits may be NULL.  Synchronous: results are ready on return. */
+int lsmrc_demod_frames_host(lsmrc_handle h, const void *h_rx, int n_frames, void *h_hconj,
+                            void *h_hsqrd, void *h_combined, void *h_bits);
+
+/* ---- per-symbol entry points (replace gpuLS::firstVector gpuLS.cu:351 and
+ *      gpuLS::demodOneSymbol :410).  rx_sym is one ring slot [A][N+C]; on_device says
+ *      where it lives.  The channel estimate stays inside the handle between calls. ---- */
+int lsmrc_first_vector(lsmrc_handle h, const void *rx_sym, int on_device);
+int lsmrc_demod_one_symbol(lsmrc_handle h, const void *rx_sym, int on_device,
+                           void *h_combined /* K complex64, host */, void *h_bits /* row bytes, host, may be NULL */);
+int lsmrc_get_channel(lsmrc_handle h, void *h_hconj /* [A][K] */, void *h_hsqrd /* [K] */);
+
+/* ---- streaming ingest from a pinned ring (replaces ShMemSymBuff::readNextSymbolCUDA /
+ *      readLastSymbolCUDA, ShMemSymBuff_gpu.hpp:373-445, plus the demod calls that follow
+ *      them).  One "lane" = one stream + device staging for one frame + pinned result
+ *      buffers.  submit() enqueues H2D of the frame's S slots (slot s at
+ *      h_slots + s*slot_stride_bytes), both kernels and the D2H of the results, and
+ *      returns at once; wait() blocks until that lane is done and hands back pointers to
+ *      the lane's pinned result buffers (valid until the lane is submitted again). ------ */
+int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void *h_slots, size_t slot_stride_bytes);
+int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void *h_first, int n_first,
+                            const void *h_second); /* frame wraps around the ring end */
+int lsmrc_ring_wait(lsmrc_handle h, int lane, const void **combined, const void **bits,
+                    const void **hconj);
+int lsmrc_ring_copy_done(lsmrc_handle h, int lane); /* blocks until the lane's H2D finished (slots reusable) */
+
+/* ---- memory and stream plumbing, so callers need no CUDA headers (replaces the raw
+ *      cudaMalloc/cudaMemcpy/cudaFree calls of gpuLS_main.cu:73-91,135-139) ------------ */
+int lsmrc_dev_alloc(lsmrc_handle h, size_t bytes, void **d_ptr);
+int lsmrc_dev_free(lsmrc_handle h, void *d_ptr);
+int lsmrc_copy_to_device(lsmrc_handle h, void *d_dst, const void *h_src, size_t bytes);
+int lsmrc_copy_to_host(lsmrc_handle h, void *h_dst, const void *d_src, size_t bytes);
+int lsmrc_host_alloc(lsmrc_handle h, size_t bytes, void **h_ptr); /* pinned */
+int lsmrc_host_free(lsmrc_handle h, void *h_ptr);
+int lsmrc_host_register(lsmrc_handle h, void *h_ptr, size_t bytes); /* pin an existing mapping (the shm ring) */
+int lsmrc_host_unregister(lsmrc_handle h, void *h_ptr);
+int lsmrc_set_stream(lsmrc_handle h, void *cuda_stream); /* run device-resident calls on a caller stream (NULL = own) */
+int lsmrc_sync(lsmrc_handle h);
+
+/* ---- instrumentation (replaces the clock() timers of ShMemSymBuff_gpu.hpp:113-257) --- */
+/* CUDA-event time of the pilot and data kernels of the most recent lsmrc_demod_frames_device
+ * call (waits for them).  Enable with lsmrc_set_timing(h, 1); off by default. */
+int lsmrc_set_timing(lsmrc_handle h, int enabled);
+int lsmrc_last_kernel_ms(lsmrc_handle h, float *pilot_ms, float *data_ms);
+/* number of kernels this library has launched through handle h since creation */
+long long lsmrc_launch_count(lsmrc_handle h);
+/* plan description, e.g. "N=1024 P=32 R2=32 R3=1 teams=4 threads=128 smem=75512" */
+int lsmrc_describe_plan(lsmrc_handle h, char *buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDM_LSMRC_H */
