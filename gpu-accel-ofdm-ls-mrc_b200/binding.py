@@ -74,6 +74,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
+    path = path or os.environ.get("LSMRC_LIB") or None
     p = path or _build.LIB_PATH
     if path is None and _build.needs_build():
         _build.build()

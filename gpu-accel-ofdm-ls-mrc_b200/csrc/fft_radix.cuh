@@ -2,13 +2,27 @@
 //
 // The receive path needs an unnormalised forward DFT per antenna row
 // (reference: cpuLS.hpp:165-174 fftOneRow / gpuLS.cu:377-380 cuFFT C2C forward).
-// A row transform is decomposed (lsmrc_kernels.cu) into register-resident
+// A row transform is decomposed (lsmrc_kernels.cuh) into register-resident
 // sub-transforms of R points per thread, joined by shared-memory exchanges.
-// This header holds the register part: a fully unrolled decimation-in-frequency
-// radix-2 recursion whose twiddles are compile-time constants, so every
-// multiply folds to an FFMA/FMUL with an immediate operand and nothing spills.
+// This header holds the register part.
 //
-// fft_dif<R>(v): in place; X[k] ends up at v[brev<R>(k)] (bit-reversed slot).
+// Blackwell-specific design: a complex value lives in one aligned 64-bit register
+// pair (re, im) and all arithmetic is issued as packed fp32x2 instructions
+// (FADD2 / FMUL2 / FFMA2, sm_100+).  Their operands take free modifiers in SASS --
+// half swap (.LO_HI), per-half negate (.NP/.PN), scalar broadcast (.F32) and
+// immediates -- so a complex add is ONE instruction and a complex multiply TWO,
+// with no shuffling of register halves.  Packed ops run at the same lane rate as
+// scalar ones (measured: tools/ubench_fp32x2.cu, 128 lane-ops/clk/SM either way),
+// so the gain is issue slots: ~2.3x fewer instructions per transform, which is
+// what bounds this kernel next to HBM.
+//
+// The transform itself is a decimation-in-time radix-2 network whose twiddled
+// butterflies use the multiply-add factorisation  a +- w*b = a +- c*(b + i*tau*b)
+// (tau = Im w / Re w, or the mirrored form when |Im w| > |Re w|): three packed FMAs
+// per butterfly instead of a complex multiply plus two adds.  All twiddles are
+// compile-time constants of W_32.
+//
+// fft_reg<R>(v): in place; input v[n] natural order, X[k] ends up at v[brev<R>(k)].
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,52 +39,75 @@ __host__ __device__ constexpr int brev(int k)
     return r;
 }
 
-// cos/sin(2*pi*j/32), j = 0..15, rounded once from double
-__device__ constexpr float kCos32[16] = {
-    1.f, 0.980785251f, 0.923879504f, 0.831469595f, 0.707106769f, 0.555570245f, 0.382683426f,
-    0.195090324f, 0.f, -0.195090324f, -0.382683426f, -0.555570245f, -0.707106769f,
-    -0.831469595f, -0.923879504f, -0.980785251f};
-__device__ constexpr float kSin32[16] = {
-    0.f, 0.195090324f, 0.382683426f, 0.555570245f, 0.707106769f, 0.831469595f, 0.923879504f,
-    0.980785251f, 1.f, 0.980785251f, 0.923879504f, 0.831469595f, 0.707106769f, 0.555570245f,
-    0.382683426f, 0.195090324f};
+// W_32^j = exp(-2*pi*i*j/32) = kWr[j] + i*kWi[j], j = 0..15, rounded once from double;
+// kTau = Wi/Wr where |Wr| >= |Wi|, kSig = Wr/Wi elsewhere (the unused entries are 0)
+__device__ constexpr float kWr[16] = {1.f, 0.980785251f, 0.923879504f, 0.831469595f, 0.707106769f, 0.555570245f,
+                                      0.382683426f, 0.195090324f, 0.f, -0.195090324f, -0.382683426f, -0.555570245f,
+                                      -0.707106769f, -0.831469595f, -0.923879504f, -0.980785251f};
+__device__ constexpr float kWi[16] = {0.f, -0.195090324f, -0.382683426f, -0.555570245f, -0.707106769f, -0.831469595f,
+                                      -0.923879504f, -0.980785251f, -1.f, -0.980785251f, -0.923879504f, -0.831469595f,
+                                      -0.707106769f, -0.555570245f, -0.382683426f, -0.195090324f};
+__device__ constexpr float kTau[16] = {0.f, -0.198912367f, -0.414213568f, -0.668178618f, -1.f, 0.f, 0.f, 0.f,
+                                       0.f, 0.f, 0.f, 0.f, 0.f, 0.668178618f, 0.414213568f, 0.198912367f};
+__device__ constexpr float kSig[16] = {0.f, 0.f, 0.f, 0.f, 0.f, -0.668178618f, -0.414213568f, -0.198912367f,
+                                       0.f, 0.198912367f, 0.414213568f, 0.668178618f, 1.f, 0.f, 0.f, 0.f};
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a * w, both runtime values: 2 packed instructions
 __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
-    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+    const float2 t = __fmul2_rn(a, make_float2(w.x, w.x));
+    return __ffma2_rn(swp(a), make_float2(-w.y, w.y), t);
+}
+// acc + a * w
+__device__ __forceinline__ float2 cmac(float2 acc, float2 a, float2 w)
+{
+    acc = __ffma2_rn(a, make_float2(w.x, w.x), acc);
+    return __ffma2_rn(swp(a), make_float2(-w.y, w.y), acc);
 }
 
-// v * exp(-2*pi*i*j32/32) for a compile-time-foldable j32 in [0,16)
-__device__ __forceinline__ float2 mul_w32(float2 v, int j32)
+// (a, b) <- (a + w*b, a - w*b), w = W_32^j32 with j32 a compile-time-foldable value in [0,16)
+__device__ __forceinline__ void bfly_dit(float2& a, float2& b, int j32)
 {
-    if (j32 == 0) return v;
-    if (j32 == 8) return make_float2(v.y, -v.x);  // * (-i)
-    if (j32 == 4) {
-        const float c = 0.707106769f;  // (1 - i)/sqrt(2)
-        return make_float2((v.x + v.y) * c, (v.y - v.x) * c);
+    if (j32 == 0) {
+        const float2 s = cadd(a, b);
+        b = csub(a, b);
+        a = s;
+    } else if (j32 == 8) {  // w = -i : w*b = (b.y, -b.x)
+        const float2 sb = swp(b);
+        const float2 s = __ffma2_rn(sb, make_float2(1.f, -1.f), a);
+        b = __ffma2_rn(sb, make_float2(-1.f, 1.f), a);
+        a = s;
+    } else if (kTau[j32] != 0.f) {  // w = c*(1 + i*tau)
+        const float tau = kTau[j32], c = kWr[j32];
+        const float2 u = __ffma2_rn(swp(b), make_float2(-tau, tau), b);
+        const float2 s = __ffma2_rn(u, make_float2(c, c), a);
+        b = __ffma2_rn(u, make_float2(-c, -c), a);
+        a = s;
+    } else {  // w = i*wi*(1 - i*sig)
+        const float sig = kSig[j32], wi = kWi[j32];
+        const float2 u = __ffma2_rn(swp(b), make_float2(sig, -sig), b);
+        const float2 su = swp(u);
+        const float2 s = __ffma2_rn(su, make_float2(-wi, wi), a);
+        b = __ffma2_rn(su, make_float2(wi, -wi), a);
+        a = s;
     }
-    if (j32 == 12) {
-        const float c = 0.707106769f;  // (-1 - i)/sqrt(2)
-        return make_float2((v.y - v.x) * c, -(v.x + v.y) * c);
-    }
-    const float wr = kCos32[j32], wi = -kSin32[j32];
-    return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
 }
 
 template <int R>
-__device__ __forceinline__ void fft_dif(float2* v)
+__device__ __forceinline__ void fft_reg(float2* v)
 {
-    if constexpr (R >= 2) {
+    // decimation in time on the bit-reversed view w[p] = v[brev(p)]
 #pragma unroll
-        for (int j = 0; j < R / 2; ++j) {
-            const float2 a = v[j], b = v[j + R / 2];
-            v[j] = cadd(a, b);
-            v[j + R / 2] = mul_w32(csub(a, b), j * (32 / R));
+    for (int len = 2; len <= R; len <<= 1) {
+#pragma unroll
+        for (int s = 0; s < R; s += len) {
+#pragma unroll
+            for (int k = 0; k < len / 2; ++k)
+                bfly_dit(v[brev<R>(s + k)], v[brev<R>(s + k + len / 2)], k * (32 / len));
         }
-        fft_dif<R / 2>(v);
-        fft_dif<R / 2>(v + R / 2);
     }
 }
 

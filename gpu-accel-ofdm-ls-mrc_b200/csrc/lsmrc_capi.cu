@@ -64,10 +64,15 @@ template <class PL, int MINB>
 cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st)
 {
     if (mode == MODE_PILOT) {
-        lsmrc_kernel<PL, MODE_PILOT, MINB><<<p.n_frames, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+        lsmrc_kernel<PL, MODE_PILOT, MINB><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
-        const long long n_work = (long long)p.n_frames * p.n_sym_work;
-        const unsigned grid = (unsigned)((n_work + PL::TEAMS - 1) / PL::TEAMS);
+        unsigned grid;
+        if (PL::H_RING) {
+            grid = (unsigned)((long long)p.n_frames * ((p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS));
+        } else {
+            const long long n_work = (long long)p.n_frames * p.n_sym_work;
+            grid = (unsigned)((n_work + PL::TEAMS - 1) / PL::TEAMS);
+        }
         lsmrc_kernel<PL, MODE_DATA, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     }
     return cudaGetLastError();
@@ -92,6 +97,32 @@ PlanOps make_ops()
     return o;
 }
 
+// tuning knobs of the headline N=1024 plan (overridable at build time for experiments)
+#ifndef LSMRC_1024_TEAMS
+#define LSMRC_1024_TEAMS 4
+#endif
+#ifndef LSMRC_1024_NBUF
+#define LSMRC_1024_NBUF 1
+#endif
+#ifndef LSMRC_1024_PFX
+#define LSMRC_1024_PFX 1
+#endif
+#ifndef LSMRC_1024_PFH
+#define LSMRC_1024_PFH 1
+#endif
+#ifndef LSMRC_1024_MINB
+#define LSMRC_1024_MINB 3
+#endif
+#ifndef LSMRC_1024_REGPF
+#define LSMRC_1024_REGPF false
+#endif
+#ifndef LSMRC_1024_XL1
+#define LSMRC_1024_XL1 false
+#endif
+#ifndef LSMRC_1024_HRING
+#define LSMRC_1024_HRING true
+#endif
+
 // One plan per FFT size (64..4096).  N/P threads own a row; see lsmrc_kernels.cuh.
 const PlanOps* find_plan(int N)
 {
@@ -100,7 +131,7 @@ const PlanOps* find_plan(int N)
         make_ops<Plan<128, 16, 8, 1, 16>, 4>(),
         make_ops<Plan<256, 16, 16, 1, 8>, 4>(),
         make_ops<Plan<512, 32, 16, 1, 8>, 3>(),
-        make_ops<Plan<1024, 32, 32, 1, 4>, 3>(),
+        make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>, LSMRC_1024_MINB>(),
         make_ops<Plan<2048, 32, 16, 4, 2>, 3>(),
         make_ops<Plan<4096, 32, 32, 4, 1>, 3>(),
     };
@@ -109,12 +140,22 @@ const PlanOps* find_plan(int N)
     return nullptr;
 }
 
+// device-side channel state for a batch of frames (internal layouts, see KernelParams)
+struct ChanState {
+    float2* hwork = nullptr;          // [frames][A][N]
+    float* hsqrd = nullptr;           // [frames][K]
+    float* epart = nullptr;           // [frames + kPilotCtaTarget][N]
+    unsigned int* counters = nullptr; // [frames], zero between launches
+    int frames = 0;
+};
+constexpr int kPilotCtaTarget = 296;  // pilot kernel: aim for >= 2 CTAs per SM when frames are few
+
 struct Lane {
+    ChanState ch;
     cudaStream_t st = nullptr;
     cudaEvent_t copied = nullptr, done = nullptr;
     float2* d_rx = nullptr;     // [max_frames][S][A][N+C]
-    float2* d_hconj = nullptr;  // [max_frames][A][K]
-    float* d_hsqrd = nullptr;   // [max_frames][K]
+    float2* d_hconj = nullptr;  // [max_frames][A][K] (reference layout, only when the caller wants it back)
     float2* d_comb = nullptr;   // [max_frames][S-1][K]
     uint8_t* d_bits = nullptr;  // [max_frames][S-1][row]
     // pinned single-frame result buffers of the ring path
@@ -142,14 +183,12 @@ struct lsmrc_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
-    // scratch channel state of the device-resident path when the caller passes NULL
-    float2* d_scr_hconj = nullptr;
-    float* d_scr_hsqrd = nullptr;
-    int scr_frames = 0;
+    // channel state of the device-resident path
+    ChanState dev_ch;
     // per-symbol path state (one frame)
+    ChanState one_ch;
     float2* d_sym = nullptr;
     float2* d_one_hconj = nullptr;
-    float* d_one_hsqrd = nullptr;
     float2* d_one_comb = nullptr;
     uint8_t* d_one_bits = nullptr;
     float2* h_one_sym = nullptr;   // pinned staging for pageable ring slots
@@ -206,28 +245,87 @@ KernelParams base_params(lsmrc_ctx* h)
     return p;
 }
 
-// pilot + data launches for n_frames whole frames
-int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frames, float2* d_hconj,
+int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
+{
+    if (c.frames >= frames) return LSMRC_OK;
+    if (quiesce) CK(h, cudaStreamSynchronize(quiesce));
+    cudaFree(c.hwork);
+    cudaFree(c.hsqrd);
+    cudaFree(c.epart);
+    cudaFree(c.counters);
+    c = ChanState();
+    const size_t N = (size_t)h->cfg.fft_size;
+    CK(h, cudaMalloc(&c.hwork, (size_t)frames * h->cfg.n_ant * N * sizeof(float2)));
+    CK(h, cudaMalloc(&c.hsqrd, (size_t)frames * h->K * sizeof(float)));
+    CK(h, cudaMalloc(&c.epart, ((size_t)frames + kPilotCtaTarget) * N * sizeof(float)));
+    CK(h, cudaMalloc(&c.counters, (size_t)frames * sizeof(unsigned int)));
+    CK(h, cudaMemset(c.counters, 0, (size_t)frames * sizeof(unsigned int)));
+    c.frames = frames;
+    return LSMRC_OK;
+}
+
+void free_chan(ChanState& c)
+{
+    cudaFree(c.hwork);
+    cudaFree(c.hsqrd);
+    cudaFree(c.epart);
+    cudaFree(c.counters);
+    c = ChanState();
+}
+
+// antenna groups per frame for the pilot kernel: enough CTAs to fill the GPU when frames are few
+int pilot_groups(const lsmrc_ctx* h, int n_frames)
+{
+    const int max_g = (h->cfg.n_ant + h->ops->teams - 1) / h->ops->teams;
+    int g = (kPilotCtaTarget + n_frames - 1) / n_frames;
+    if (g > max_g) g = max_g;
+    if (g < 1) g = 1;
+    return g;
+}
+
+int launch_pilot(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, float2* d_hconj, float* d_hsqrd)
+{
+    p.first_sym = 0;
+    p.n_sym_work = 1;
+    p.hwork = ch.hwork;
+    p.hconj = d_hconj;
+    p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
+    p.n_groups = pilot_groups(h, p.n_frames);
+    p.epart = ch.epart;
+    p.counters = ch.counters;
+    CK(h, h->ops->launch(MODE_PILOT, p, st));
+    h->launches++;
+    return LSMRC_OK;
+}
+
+int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, float* d_hsqrd, int first_sym, int n_sym_work)
+{
+    p.first_sym = first_sym;
+    p.n_sym_work = n_sym_work;
+    p.hwork = ch.hwork;
+    p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
+    p.n_groups = 1;
+    CK(h, h->ops->launch(MODE_DATA, p, st));
+    h->launches++;
+    return LSMRC_OK;
+}
+
+// pilot + data launches for n_frames whole frames (ch must hold >= n_frames)
+int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frames, ChanState& ch, float2* d_hconj,
                   float* d_hsqrd, float2* d_comb, uint8_t* d_bits, bool timed)
 {
     KernelParams p = base_params(h);
     p.rx = d_rx;
     p.n_frames = n_frames;
-    p.hconj = d_hconj;
-    p.hsqrd = d_hsqrd;
     p.combined = d_comb;
     p.bits = d_bits;
     if (timed) CK(h, cudaEventRecord(h->ev0, st));
-    p.first_sym = 0;
-    p.n_sym_work = 1;
-    CK(h, h->ops->launch(MODE_PILOT, p, st));
-    h->launches++;
+    int rc = launch_pilot(h, st, p, ch, d_hconj, d_hsqrd);
+    if (rc != LSMRC_OK) return rc;
     if (timed) CK(h, cudaEventRecord(h->ev1, st));
     if (h->cfg.n_sym > 1) {
-        p.first_sym = 1;
-        p.n_sym_work = h->cfg.n_sym - 1;
-        CK(h, h->ops->launch(MODE_DATA, p, st));
-        h->launches++;
+        rc = launch_data(h, st, p, ch, d_hsqrd, 1, h->cfg.n_sym - 1);
+        if (rc != LSMRC_OK) return rc;
     }
     if (timed) {
         CK(h, cudaEventRecord(h->ev2, st));
@@ -275,7 +373,10 @@ int alloc_lane(lsmrc_ctx* h, Lane& L)
     CK(h, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
     CK(h, cudaMalloc(&L.d_rx, F * h->frame_elems * sizeof(float2)));
     CK(h, cudaMalloc(&L.d_hconj, F * (size_t)c.n_ant * h->K * sizeof(float2)));
-    CK(h, cudaMalloc(&L.d_hsqrd, F * (size_t)h->K * sizeof(float)));
+    {
+        const int rc = ensure_chan(h, L.ch, c.max_frames, nullptr);
+        if (rc != LSMRC_OK) return rc;
+    }
     CK(h, cudaMalloc(&L.d_comb, F * nd * h->K * sizeof(float2)));
     CK(h, cudaMalloc(&L.d_bits, F * nd * h->row_bytes));
     CK(h, cudaMallocHost(&L.h_comb, nd * h->K * sizeof(float2)));
@@ -289,7 +390,7 @@ void free_lane(Lane& L)
     if (L.st) cudaStreamSynchronize(L.st);
     cudaFree(L.d_rx);
     cudaFree(L.d_hconj);
-    cudaFree(L.d_hsqrd);
+    free_chan(L.ch);
     cudaFree(L.d_comb);
     cudaFree(L.d_bits);
     cudaFreeHost(L.h_comb);
@@ -322,7 +423,10 @@ int ensure_symbol_state(lsmrc_ctx* h)
     const lsmrc_config& c = h->cfg;
     CK(h, cudaMalloc(&h->d_sym, h->slot_elems * sizeof(float2)));
     CK(h, cudaMalloc(&h->d_one_hconj, (size_t)c.n_ant * h->K * sizeof(float2)));
-    CK(h, cudaMalloc(&h->d_one_hsqrd, (size_t)h->K * sizeof(float)));
+    {
+        const int rc = ensure_chan(h, h->one_ch, 1, nullptr);
+        if (rc != LSMRC_OK) return rc;
+    }
     CK(h, cudaMalloc(&h->d_one_comb, (size_t)h->K * sizeof(float2)));
     CK(h, cudaMalloc(&h->d_one_bits, h->row_bytes));
     CK(h, cudaMallocHost(&h->h_one_sym, h->slot_elems * sizeof(float2)));
@@ -457,11 +561,10 @@ int lsmrc_destroy(lsmrc_handle h)
     for (Lane& L : h->lanes) free_lane(L);
     cudaFree(h->d_tw);
     cudaFree(h->d_pilot_bin);
-    cudaFree(h->d_scr_hconj);
-    cudaFree(h->d_scr_hsqrd);
+    free_chan(h->dev_ch);
+    free_chan(h->one_ch);
     cudaFree(h->d_sym);
     cudaFree(h->d_one_hconj);
-    cudaFree(h->d_one_hsqrd);
     cudaFree(h->d_one_comb);
     cudaFree(h->d_one_bits);
     cudaFreeHost(h->h_one_sym);
@@ -523,21 +626,13 @@ int lsmrc_demod_frames_device(lsmrc_handle h, const void* d_rx, int n_frames, vo
     if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
     if (n_frames == 0) return LSMRC_OK;
     CK(h, cudaSetDevice(h->cfg.device));
-    if ((!d_hconj || !d_hsqrd) && h->scr_frames < n_frames) {
-        CK(h, cudaStreamSynchronize(compute_stream(h)));
-        cudaFree(h->d_scr_hconj);
-        cudaFree(h->d_scr_hsqrd);
-        h->d_scr_hconj = nullptr;
-        h->d_scr_hsqrd = nullptr;
-        h->scr_frames = 0;
-        CK(h, cudaMalloc(&h->d_scr_hconj, (size_t)n_frames * h->cfg.n_ant * h->K * sizeof(float2)));
-        CK(h, cudaMalloc(&h->d_scr_hsqrd, (size_t)n_frames * h->K * sizeof(float)));
-        h->scr_frames = n_frames;
+    {
+        const int rc = ensure_chan(h, h->dev_ch, n_frames, compute_stream(h));
+        if (rc != LSMRC_OK) return rc;
     }
-    float2* hc = d_hconj ? static_cast<float2*>(d_hconj) : h->d_scr_hconj;
-    float* hs = d_hsqrd ? static_cast<float*>(d_hsqrd) : h->d_scr_hsqrd;
-    return launch_frames(h, compute_stream(h), static_cast<const float2*>(d_rx), n_frames, hc, hs,
-                         static_cast<float2*>(d_combined), static_cast<uint8_t*>(d_bits), h->timing);
+    return launch_frames(h, compute_stream(h), static_cast<const float2*>(d_rx), n_frames, h->dev_ch,
+                         static_cast<float2*>(d_hconj), static_cast<float*>(d_hsqrd), static_cast<float2*>(d_combined),
+                         static_cast<uint8_t*>(d_bits), h->timing);
 }
 
 int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,
@@ -570,7 +665,8 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
         Lane& L = h->lanes[(size_t)chunk_idx % h->lanes.size()];
         const char* src = static_cast<const char*>(h_rx) + (size_t)f0 * rx_fb;
         CK(h, cudaMemcpyAsync(L.d_rx, src, rx_fb * nf, cudaMemcpyHostToDevice, L.st));
-        rc = launch_frames(h, L.st, L.d_rx, nf, L.d_hconj, L.d_hsqrd, L.d_comb, h_bits ? L.d_bits : nullptr, false);
+        rc = launch_frames(h, L.st, L.d_rx, nf, L.ch, h_hconj ? L.d_hconj : nullptr, nullptr, L.d_comb,
+                           h_bits ? L.d_bits : nullptr, false);
         if (rc != LSMRC_OK) return rc;
         if (nd > 0)
             CK(h, cudaMemcpyAsync(static_cast<char*>(h_combined) + (size_t)f0 * cb_fb, L.d_comb, cb_fb * nf,
@@ -582,7 +678,7 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
             CK(h, cudaMemcpyAsync(static_cast<char*>(h_hconj) + (size_t)f0 * hc_fb, L.d_hconj, hc_fb * nf,
                                   cudaMemcpyDeviceToHost, L.st));
         if (h_hsqrd)
-            CK(h, cudaMemcpyAsync(static_cast<char*>(h_hsqrd) + (size_t)f0 * hs_fb, L.d_hsqrd, hs_fb * nf,
+            CK(h, cudaMemcpyAsync(static_cast<char*>(h_hsqrd) + (size_t)f0 * hs_fb, L.ch.hsqrd, hs_fb * nf,
                                   cudaMemcpyDeviceToHost, L.st));
     }
     for (Lane& L : h->lanes) CK(h, cudaStreamSynchronize(L.st));
@@ -602,13 +698,8 @@ int lsmrc_first_vector(lsmrc_handle h, const void* rx_sym, int on_device)
     p.rx = d_in;
     p.frame_stride = 0;
     p.sym_stride = 0;
-    p.first_sym = 0;
-    p.n_sym_work = 1;
     p.n_frames = 1;
-    p.hconj = h->d_one_hconj;
-    p.hsqrd = h->d_one_hsqrd;
-    CK(h, h->ops->launch(MODE_PILOT, p, h->own_stream));
-    h->launches++;
+    if ((rc = launch_pilot(h, h->own_stream, p, h->one_ch, h->d_one_hconj, nullptr)) != LSMRC_OK) return rc;
     h->have_channel = true;
     return LSMRC_OK;
 }
@@ -625,16 +716,11 @@ int lsmrc_demod_one_symbol(lsmrc_handle h, const void* rx_sym, int on_device, vo
     p.rx = d_in;
     p.frame_stride = 0;
     p.sym_stride = 0;
-    p.first_sym = 0;
-    p.n_sym_work = 1;
     p.n_frames = 1;
-    p.hconj = h->d_one_hconj;
-    p.hsqrd = h->d_one_hsqrd;
     p.combined = h->d_one_comb;
     p.bits = h->d_one_bits;
     cudaStream_t st = h->own_stream;
-    CK(h, h->ops->launch(MODE_DATA, p, st));
-    h->launches++;
+    if ((rc = launch_data(h, st, p, h->one_ch, nullptr, 0, 1)) != LSMRC_OK) return rc;
     CK(h, cudaMemcpyAsync(h->h_one_comb, h->d_one_comb, (size_t)h->K * sizeof(float2), cudaMemcpyDeviceToHost, st));
     if (h_bits) CK(h, cudaMemcpyAsync(h->h_one_bits, h->d_one_bits, h->row_bytes, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
@@ -650,7 +736,7 @@ int lsmrc_get_channel(lsmrc_handle h, void* h_hconj, void* h_hsqrd)
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->own_stream));
     if (h_hconj) CK(h, cudaMemcpy(h_hconj, h->d_one_hconj, (size_t)h->cfg.n_ant * h->K * sizeof(float2), cudaMemcpyDeviceToHost));
-    if (h_hsqrd) CK(h, cudaMemcpy(h_hsqrd, h->d_one_hsqrd, (size_t)h->K * sizeof(float), cudaMemcpyDeviceToHost));
+    if (h_hsqrd) CK(h, cudaMemcpy(h_hsqrd, h->one_ch.hsqrd, (size_t)h->K * sizeof(float), cudaMemcpyDeviceToHost));
     return LSMRC_OK;
 }
 
@@ -661,7 +747,7 @@ static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L)
     const lsmrc_config& c = h->cfg;
     const size_t nd = (size_t)(c.n_sym - 1);
     CK(h, cudaEventRecord(L.copied, L.st));
-    int rc = launch_frames(h, L.st, L.d_rx, 1, L.d_hconj, L.d_hsqrd, L.d_comb, L.d_bits, false);
+    int rc = launch_frames(h, L.st, L.d_rx, 1, L.ch, L.d_hconj, nullptr, L.d_comb, L.d_bits, false);
     if (rc != LSMRC_OK) return rc;
     if (nd > 0) {
         CK(h, cudaMemcpyAsync(L.h_comb, L.d_comb, nd * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));

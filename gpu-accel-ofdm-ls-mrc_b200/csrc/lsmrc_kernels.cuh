@@ -52,9 +52,17 @@ struct KernelParams {
     int n_sym_work; // symbols handled per frame by this launch (1 for pilot, S-1 for data)
     int n_frames;
     int qam_bits;
-    // per-frame state: Hconj [F][A][K] (conj of the LS estimate, bin order) and sum|H|^2 [F][K]
+    // per-frame channel state.  hwork [F][A][N]: conj of the LS estimate indexed by FFT bin
+    // (entry 0 unused), 16-byte aligned rows -- the layout the data kernel streams.  hconj
+    // [F][A][K] is the reference's layout (bin k+1 at index k, gpuLS.cu:158-182), written only
+    // when the caller asks for it (may be nullptr).  hsqrd [F][K] = sum_a |H|^2.
+    float2* hwork;
     float2* hconj;
     float* hsqrd;
+    // pilot kernel only: antenna groups per frame, partial-energy scratch [F][G][N], arrival counters [F]
+    int n_groups;
+    float* epart;
+    unsigned int* counters;
     const float2* pilot_bin;  // X in FFT-bin order, K entries (bin k+1 at index k)
     // outputs of MODE_DATA
     float2* combined;  // [F][n_sym_work][K], ascending frequency
@@ -63,10 +71,23 @@ struct KernelParams {
     const float2* twiddles;  // plan table: tw1 [(P-1)][T] then tw2 [(R2-1)][R3]
 };
 
-template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2>
+template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, bool REG_PF_ = false, bool X_L1_ = false, bool H_RING_ = false>
 struct Plan {
+    // REG_PF: data kernel loads row a+1 into registers while row a is in stage 2/3 + MRC
+    static constexpr bool REG_PF = REG_PF_;
+    // X_L1: prefetch the antenna-samples into L1 (and load them with L1 allocation) instead of L2
+    static constexpr bool X_L1 = X_L1_;
+    // H_RING: the TEAMS teams of a CTA work on TEAMS data symbols of ONE frame and share each
+    // Hconj row through a shared-memory ring filled by bulk async copies (TMA) on mbarriers
+    static constexpr bool H_RING = H_RING_;
+    static constexpr int H_STAGES = 3;
+    static constexpr int HRING = H_RING_ ? H_STAGES * N_ : 0;  // complex elements
+    // PF_X: rows ahead whose antenna-samples are prefetched into L2; PF_H: rows ahead whose
+    // Hconj row is prefetched into L1 (0 = off)
+    static constexpr int PF_X = PF_X_, PF_H = PF_H_;
     static constexpr int N = N_, P = P_, R2 = R2_, R3 = R3_, TEAMS = TEAMS_, NBUF = NBUF_;
     static constexpr int T = N / P;        // threads per team == M1 (points per row of the tile)
+    static constexpr bool T_OK = (N_ / P_) <= 32 || true;
     static constexpr int ROW = T + 1;      // padded tile row (complex elements)
     static constexpr int NB2 = P / R2;     // stage-2 butterflies per thread
     static constexpr int NB3 = P / R3;     // stage-3 butterflies per thread (R3 > 1)
@@ -77,7 +98,8 @@ struct Plan {
     static constexpr int TW2 = (R3 > 1) ? (R2 - 1) * R3 : 0;
     static constexpr int TWN = TW1 + TW2;
     static constexpr int TILE = P * ROW;   // complex elements per tile
-    static constexpr size_t SMEM_BYTES = sizeof(float2) * (size_t)(TWN + TEAMS * NBUF * TILE);
+    static constexpr size_t SMEM_BYTES = sizeof(float2) * (size_t)(TWN + HRING + TEAMS * NBUF * TILE);
+    static_assert(!H_RING_ || (TWN % 2 == 0 && T_OK), "ring rows must stay 16-byte aligned");
     static_assert(P * R2 * R3 == N, "plan must factor N");
     static_assert(P >= R2 && P >= R3, "thread must own whole butterflies");
     static_assert(THREADS <= 1024, "block too large");
@@ -90,6 +112,66 @@ __device__ __forceinline__ float2 ld_stream(const float2* p)
     float2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
+}
+
+// software prefetch hints: pull lines that a later iteration will read into L2 / L1 so that
+// the demand loads of that iteration see cache latency instead of HBM latency
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// each thread of a team touches every 128-byte line of [base, base + n_elems) once
+template <int T, bool TO_L1>
+__device__ __forceinline__ void prefetch_row(const float2* base, int n_elems, int t)
+{
+    constexpr int PER_LINE = 128 / (int)sizeof(float2);
+#pragma unroll 4
+    for (int e = t * PER_LINE; e < n_elems; e += T * PER_LINE) {
+        if (TO_L1) prefetch_l1(base + e);
+        else prefetch_l2(base + e);
+    }
+}
+
+// ---- mbarrier + bulk async copy (TMA, 1-D) primitives ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes and addresses multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 template <class PL>
@@ -127,27 +209,39 @@ __device__ __forceinline__ unsigned demap_symbol(float re, float im, int qam_bit
     return v;
 }
 
-// One N-point forward DFT of the row starting at `x` (CP already skipped), the
-// team's P*T outputs handed to `sink(slot, bin, value)` where slot in [0,P) is
-// the thread-local accumulator index and bin = c + (N/RL)*j is the FFT bin.
+template <class PL>
+__device__ __forceinline__ void row_load(float2 (&v)[PL::P], const float2* __restrict__ x, int t)
+{
+#pragma unroll
+    for (int n1 = 0; n1 < PL::P; ++n1) {
+#ifdef LSMRC_FAKE_X  // experiment only: no global traffic for x (results are garbage)
+        v[n1] = make_float2(__int_as_float(0x3f800000 + n1 + t), (float)n1);
+        asm volatile("" : "+f"(v[n1].x), "+f"(v[n1].y));
+#else
+        v[n1] = PL::X_L1 ? __ldg(x + n1 * PL::T + t) : ld_stream(x + n1 * PL::T + t);
+#endif
+    }
+}
+
+// One N-point forward DFT of the row whose samples are already in `v` (v[n1] = x[n1*T + t],
+// CP skipped); the team's P*T outputs are handed to `sink(slot, bin, value)` where slot in
+// [0,P) is the thread-local accumulator index and bin = c + (N/RL)*j is the FFT bin.
+// If x_next != nullptr the next row is loaded into `v` as soon as stage 1 has consumed it,
+// so its HBM latency hides behind stage 2/3 and the MRC of this row (register prefetch).
 template <class PL, class Sink>
-__device__ __forceinline__ void row_fft(const float2* __restrict__ x, float2* __restrict__ tile,
-                                        const float2* __restrict__ s_tw1,
+__device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __restrict__ x_next,
+                                        float2* __restrict__ tile, const float2* __restrict__ s_tw1,
                                         const float2* __restrict__ s_tw2, int t, int team, Sink&& sink)
 {
     constexpr int P = PL::P, T = PL::T, ROW = PL::ROW, R2 = PL::R2, R3 = PL::R3;
-    {
-        float2 v[P];
+    fft_reg<P>(v);
 #pragma unroll
-        for (int n1 = 0; n1 < P; ++n1) v[n1] = ld_stream(x + n1 * T + t);
-        fft_dif<P>(v);
-#pragma unroll
-        for (int k1 = 0; k1 < P; ++k1) {
-            float2 val = v[brev<P>(k1)];
-            if (k1 > 0) val = cmul(val, s_tw1[(k1 - 1) * T + t]);
-            tile[k1 * ROW + t] = val;
-        }
+    for (int k1 = 0; k1 < P; ++k1) {
+        float2 val = v[brev<P>(k1)];
+        if (k1 > 0) val = cmul(val, s_tw1[(k1 - 1) * T + t]);
+        tile[k1 * ROW + t] = val;
     }
+    if (x_next != nullptr) row_load<PL>(v, x_next, t);
     team_sync<PL>(team);
 #pragma unroll
     for (int i = 0; i < PL::NB2; ++i) {
@@ -157,7 +251,7 @@ __device__ __forceinline__ void row_fft(const float2* __restrict__ x, float2* __
         float2* col = tile + k1 * ROW + m2;
 #pragma unroll
         for (int n2 = 0; n2 < R2; ++n2) u[n2] = col[n2 * R3];
-        fft_dif<R2>(u);
+        fft_reg<R2>(u);
         if constexpr (R3 == 1) {
 #pragma unroll
             for (int k2 = 0; k2 < R2; ++k2) sink(i * R2 + k2, b + (PL::N / R2) * k2, u[brev<R2>(k2)]);
@@ -180,7 +274,7 @@ __device__ __forceinline__ void row_fft(const float2* __restrict__ x, float2* __
             const float2* src = tile + k1 * ROW + k2 * R3;
 #pragma unroll
             for (int m2 = 0; m2 < R3; ++m2) w[m2] = src[m2];
-            fft_dif<R3>(w);
+            fft_reg<R3>(w);
 #pragma unroll
             for (int k3 = 0; k3 < R3; ++k3) sink(i * R3 + k3, c + (PL::N / R3) * k3, w[brev<R3>(k3)]);
         }
@@ -192,10 +286,12 @@ template <class PL, int MODE, int MINB>
 __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelParams p)
 {
     constexpr int N = PL::N, P = PL::P, T = PL::T, K = N - 1;
-    extern __shared__ float2 smem[];
+    constexpr int PF_X = PL::PF_X, PF_H = PL::PF_H;
+    extern __shared__ __align__(16) float2 smem[];
     float2* s_tw1 = smem;
     float2* s_tw2 = smem + PL::TW1;
-    float2* s_tiles = smem + PL::TWN;
+    float2* s_hring = smem + PL::TWN;
+    float2* s_tiles = smem + PL::TWN + PL::HRING;
 
     for (int i = threadIdx.x; i < PL::TWN; i += PL::THREADS) smem[i] = p.twiddles[i];
     __syncthreads();
@@ -205,10 +301,13 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
     float2* my_tiles = s_tiles + team * (PL::NBUF * PL::TILE);
 
     if constexpr (MODE == MODE_PILOT) {
-        // one CTA per frame; antennas dealt round-robin to the teams
-        const int f = blockIdx.x;
+        // CTA (f, g): frame f, antenna group g of n_groups; inside the CTA the antennas of the
+        // group are dealt round-robin to the teams
+        const int f = blockIdx.x / p.n_groups;
+        const int g = blockIdx.x % p.n_groups;
         const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)p.first_sym * p.sym_stride + p.cp;
-        float2* hc_frame = p.hconj + (long long)f * p.n_ant * K;
+        float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+        float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
         float e[P];
         float2 xp[P];   // pilot value per owned bin
         float xden[P];  // |X|^2, hoisted: cpuLS.hpp:240-241 recomputes it per element
@@ -220,26 +319,34 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
             xden[sl] = xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y;
         }
-        const int n_iter = (p.n_ant + PL::TEAMS - 1) / PL::TEAMS;
+        const int per_iter = p.n_groups * PL::TEAMS;
+        const int n_iter = (p.n_ant + per_iter - 1) / per_iter;
         for (int it = 0; it < n_iter; ++it) {
-            const int a_raw = it * PL::TEAMS + team;
+            const int a_raw = (it * p.n_groups + g) * PL::TEAMS + team;
             const bool a_ok = a_raw < p.n_ant;
             const int a = a_ok ? a_raw : p.n_ant - 1;
             float2* tile = my_tiles + (PL::NBUF == 2 ? (it & 1) * PL::TILE : 0);
-            float2* hc_row = hc_frame + (long long)a * K;
-            row_fft<PL>(x0 + (long long)a * p.ant_stride, tile, s_tw1, s_tw2, t, team,
+            float2* hw_row = hw_frame + (long long)a * N;
+            float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
+            float2 v[P];
+            row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
+            row_fft<PL>(v, nullptr, tile, s_tw1, s_tw2, t, team,
                         [&](int sl, int bin, float2 z) {
                             // LS estimate, naive complex division of cpuLS.hpp:233-244, then conj (:303-307)
                             const float2 X = xp[sl];
                             const float re = (z.x * X.x + z.y * X.y) / xden[sl];
                             const float im = (z.y * X.x - z.x * X.y) / xden[sl];
-                            if (a_ok && bin > 0) {
-                                hc_row[bin - 1] = make_float2(re, -im);
-                                e[sl] += re * re + im * im;  // cpuLS.hpp:211-228
+                            if (a_ok) {
+                                const float2 hc = (bin > 0) ? make_float2(re, -im) : make_float2(0.f, 0.f);
+                                hw_row[bin] = hc;
+                                if (bin > 0) {
+                                    if (hc_row) hc_row[bin - 1] = hc;
+                                    e[sl] += re * re + im * im;  // cpuLS.hpp:211-228
+                                }
                             }
                         });
         }
-        // deterministic cross-team sum of the energy partials
+        // deterministic cross-team sum of the energy partials, then cross-group by the last CTA
         __syncthreads();
         float* s_e = reinterpret_cast<float*>(s_tiles);  // [TEAMS][N]
 #pragma unroll
@@ -249,36 +356,127 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             s_e[team * N + bin] = e[sl];
         }
         __syncthreads();
-        const int n_live = p.n_ant < PL::TEAMS ? p.n_ant : PL::TEAMS;
+        float* dst = (p.n_groups == 1) ? (p.hsqrd + (long long)f * K - 1) : (p.epart + ((long long)f * p.n_groups + g) * N);
         for (int bin = 1 + threadIdx.x; bin < N; bin += PL::THREADS) {
             float acc = s_e[bin];
-            for (int tm = 1; tm < n_live; ++tm) acc += s_e[tm * N + bin];
-            p.hsqrd[(long long)f * K + bin - 1] = acc;
+            for (int tm = 1; tm < PL::TEAMS; ++tm) acc += s_e[tm * N + bin];
+            dst[bin] = acc;
+        }
+        if (p.n_groups > 1) {
+            __shared__ unsigned int s_last;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int prev = atomicAdd(p.counters + f, 1u);
+                s_last = (prev == (unsigned)p.n_groups - 1u);
+                if (s_last) p.counters[f] = 0u;  // self-reset for the next launch
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const float* ep = p.epart + (long long)f * p.n_groups * N;
+                for (int bin = 1 + threadIdx.x; bin < N; bin += PL::THREADS) {
+                    float acc = __ldcg(ep + bin);
+                    for (int gg = 1; gg < p.n_groups; ++gg) acc += __ldcg(ep + (long long)gg * N + bin);
+                    p.hsqrd[(long long)f * K + bin - 1] = acc;
+                }
+            }
         }
     } else {
         // one team per (frame, data symbol); loop over all antennas, accumulate in registers
-        const long long n_work = (long long)p.n_frames * p.n_sym_work;
-        long long work = (long long)blockIdx.x * PL::TEAMS + team;
-        const bool valid = work < n_work;
-        if (!valid) work = n_work - 1;
-        const int f = (int)(work / p.n_sym_work);
-        const int s = (int)(work % p.n_sym_work);
+        int f, s;
+        bool valid;
+        if constexpr (PL::H_RING) {
+            const int groups = (p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS;
+            f = blockIdx.x / groups;
+            s = (blockIdx.x % groups) * PL::TEAMS + team;
+            valid = s < p.n_sym_work;
+            if (!valid) s = p.n_sym_work - 1;
+        } else {
+            const long long n_work = (long long)p.n_frames * p.n_sym_work;
+            long long work = (long long)blockIdx.x * PL::TEAMS + team;
+            valid = work < n_work;
+            if (!valid) work = n_work - 1;
+            f = (int)(work / p.n_sym_work);
+            s = (int)(work % p.n_sym_work);
+        }
         const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)(p.first_sym + s) * p.sym_stride + p.cp;
-        const float2* hc_frame = p.hconj + (long long)f * p.n_ant * K;
+        const float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
         float2 acc[P];
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) acc[sl] = make_float2(0.f, 0.f);
 
+        // Hconj ring: stage r%3 holds row r; full[] completes on the copy's bytes, empty[] when
+        // every team has consumed the row.  Thread 0 keeps one row in flight ahead of the row
+        // being consumed; a stage is only refilled two rows after its last use, so the producer
+        // practically never waits on a straggling team.
+        __shared__ __align__(8) uint64_t bar_full[PL::H_STAGES], bar_empty[PL::H_STAGES];
+        constexpr uint32_t ROW_BYTES = N * sizeof(float2);
+        if constexpr (PL::H_RING) {
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < PL::H_STAGES; ++i) {
+                    mbar_init(&bar_full[i], 1);
+                    mbar_init(&bar_empty[i], PL::TEAMS);
+                }
+                mbar_fence_init();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar_full[0], ROW_BYTES);
+                bulk_g2s(s_hring, hw_frame, ROW_BYTES, &bar_full[0]);
+            }
+        }
+
+        float2 v[P];
+        if (PL::REG_PF) row_load<PL>(v, x0, t);
         for (int a = 0; a < p.n_ant; ++a) {
             float2* tile = my_tiles + (PL::NBUF == 2 ? (a & 1) * PL::TILE : 0);
-            const float2* hc_row = hc_frame + (long long)a * K;
-            row_fft<PL>(x0 + (long long)a * p.ant_stride, tile, s_tw1, s_tw2, t, team,
+            const float2* hw_row = hw_frame + (long long)a * N;
+            if constexpr (PL::H_RING) {
+                const int r = a + 1;
+                if (threadIdx.x == 0 && r < p.n_ant) {
+                    const int sr = r % PL::H_STAGES, use = r / PL::H_STAGES;
+                    if (use > 0) mbar_wait(&bar_empty[sr], (uint32_t)((use - 1) & 1));
+                    mbar_expect_tx(&bar_full[sr], ROW_BYTES);
+                    bulk_g2s(s_hring + sr * N, hw_frame + (long long)r * N, ROW_BYTES, &bar_full[sr]);
+                }
+                __syncwarp();
+            }
+            const float2* x_next = nullptr;
+            if (PL::REG_PF) {
+                if (a + 1 < p.n_ant) x_next = x0 + (long long)(a + 1) * p.ant_stride;
+            } else {
+                row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
+            }
+            if (PF_X > 0 && a + PF_X < p.n_ant)
+                prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X) * p.ant_stride, N, t);
+            if (!PL::H_RING && PF_H > 0 && a + PF_H < p.n_ant) prefetch_row<T, true>(hw_row + (long long)PF_H * N, N, t);
+            const int st = a % PL::H_STAGES;
+            const float2* h_src = PL::H_RING ? (s_hring + st * N) : hw_row;
+            bool h_ready = !PL::H_RING;
+            row_fft<PL>(v, x_next, tile, s_tw1, s_tw2, t, team,
                         [&](int sl, int bin, float2 y) {
                             // cpuLS.hpp:187-208: acc += Y * Hconj
-                            const float2 h = __ldg(hc_row + (bin > 0 ? bin - 1 : 0));
-                            acc[sl].x += y.x * h.x - y.y * h.y;
-                            acc[sl].y += y.x * h.y + y.y * h.x;
+                            if constexpr (PL::H_RING) {
+                                if (!h_ready) {
+                                    mbar_wait(&bar_full[st], (uint32_t)((a / PL::H_STAGES) & 1));
+                                    h_ready = true;
+                                }
+                                acc[sl] = cmac(acc[sl], h_src[bin], y);
+                            } else {
+#ifdef LSMRC_FAKE_H  // experiment only
+                                float2 h = make_float2(1.f + sl, 0.5f);
+                                asm volatile("" : "+f"(h.x), "+f"(h.y));
+#else
+                                const float2 h = __ldg(h_src + bin);
+#endif
+                                acc[sl] = cmac(acc[sl], h, y);
+                            }
                         });
+            if constexpr (PL::H_RING) {
+                __syncwarp();
+                if (t == 0) mbar_arrive(&bar_empty[st]);
+            }
         }
 
         // epilogue: normalise (cpuLS.hpp:364-367), reorder (cpuLS.hpp:135-149), demap, pack
@@ -292,7 +490,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             const int bin = t + T * i + (N / PL::RL) * j;
             if (bin > 0) {
                 const float e = e_row[bin - 1];
-                const float2 o = make_float2(acc[sl].x / e, acc[sl].y / e);
+                // 2-ulp reciprocal-multiply; well inside the 1e-5 parity tolerance
+                const float2 o = make_float2(__fdividef(acc[sl].x, e), __fdividef(acc[sl].y, e));
                 const int pos = (bin < N / 2) ? (bin - 1 + N / 2) : (bin - N / 2);
                 if (valid) out_row[pos] = o;
                 s_idx[pos] = (uint8_t)demap_symbol(o.x, o.y, p.qam_bits);
@@ -303,14 +502,14 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             uint8_t* bits_row = p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes;
             const int b = p.qam_bits;
             for (int byte = t; byte < p.bits_row_bytes; byte += T) {
-                unsigned v = 0;
+                unsigned v8 = 0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int pos = byte * 8 + q;
                     const int sym = pos / b, bit = pos - sym * b;
-                    if (sym < K) v |= ((s_idx[sym] >> bit) & 1u) << q;
+                    if (sym < K) v8 |= ((s_idx[sym] >> bit) & 1u) << q;
                 }
-                if (valid) bits_row[byte] = (uint8_t)v;
+                if (valid) bits_row[byte] = (uint8_t)v8;
             }
         }
     }

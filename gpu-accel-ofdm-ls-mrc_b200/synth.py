@@ -74,6 +74,8 @@ def make_frames(n_frames, n_ant, fft_size, cp_len, n_sym, qam_bits, snr_db=None,
     tx_bin[:, 1:, 1:] = asc_to_bin(data_asc)
     if channel == "identity":
         h = np.ones((F, A, K), np.complex128)
+    elif channel == "unit":  # unit modulus, random phase: no deep fades (for single-antenna cases)
+        h = np.exp(2j * np.pi * rng.random((F, A, K)))
     else:
         h = (rng.standard_normal((F, A, K)) + 1j * rng.standard_normal((F, A, K))) / np.sqrt(2.0)
     hfull = np.zeros((F, A, N), np.complex128)
