@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the uplink OFDM receiver hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--config c2]
+
+Metric (BASELINE.json): LS+MRC antenna-samples/s.  One antenna-sample = one complex64 time
+sample from one antenna, cyclic prefix included (A*S*(N+C) per frame).  A "step" is one pass
+of the whole hot path (pilot kernel + data kernel) over one batch of F synthetic frames per
+GPU.  Default workload: configs[1] = c2 (1024-pt FFT, 64 antennas, 1 pilot + 100 data
+symbols, 16-QAM); the 10k-frame batch (563 GB) does not fit HBM, so it is processed in
+resident chunks of F frames -- one chunk = one step (weak scaling: F frames per GPU per step).
+
+Printed JSON line (rank 0): value = whole-job antenna-samples/s with inputs resident in HBM;
+e2e = the same metric through the public host-buffer call (lsmrc_demod_frames_host: pinned host
+buffers, H2D and D2H inside the timed region); roofline = algorithmic HBM bytes of the dominant
+(data) kernel / its CUDA-event duration vs the measured copy bandwidth; cpu_baseline = the CPU
+oracle (port of the reference's cpuLS path) timed on this box's host cores on a bounded sample.
+
+--impl reference times the reference's CPU path (the oracle port, all host threads) on the
+same config and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ls_mrc_antenna_samples_per_s"
+UNIT = "antenna-samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (0 = config default)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU (0 = default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# frames per step per GPU: large enough that one step's input exceeds the 126 MB L2 many times over
+DEFAULT_FRAMES = {"c1": 65536, "c2": 64, "c3": 96, "c4": 24, "c5": 16384}
+DEFAULT_E2E_FRAMES = {"c1": 16384, "c2": 16, "c3": 32, "c4": 8, "c5": 8192}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # median over the samples taken under load (power well above idle)
+        loaded = [s for s, p in zip(sm, pw) if p > 0.6 * max(pw)] if pw else sm
+        return {"sm_mhz": statistics.median(loaded) if loaded else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic_per_frame(cfg_name):
+    """dram bytes per frame of the data kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p)).get(cfg_name)
+            if d:
+                return float(d["data_kernel_dram_bytes"]) / float(d["frames"])
+        except Exception:
+            pass
+    return None
+
+
+def cpu_baseline(cfg, n_threads, budget_s=12.0):
+    """oracle port (restated cpuLS.hpp path + demap) timed on the host cores, bounded sample"""
+    import numpy as np
+    from oracle import oracle_py
+
+    oracle_py.build(ref=False)
+    import ofdm_b200 as m
+
+    rng = np.random.default_rng(7)
+    A, N, C, S = cfg.n_ant, cfg.fft_size, cfg.cp_len, cfg.n_sym
+    pilot = m.synth.make_pilot(cfg.K, cfg.seed)
+
+    def make(F):
+        x = rng.standard_normal((F, S, A, N + C, 2), dtype=np.float32)
+        return x.view(np.complex64)[..., 0]
+
+    # calibrate on one frame per thread
+    F0 = n_threads
+    rx = make(F0)
+    t0 = time.perf_counter()
+    oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
+    t_cal = time.perf_counter() - t0
+    reps = max(1, min(int(budget_s / max(t_cal, 1e-3)), 2000))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
+    dt = time.perf_counter() - t0
+    frames = F0 * reps
+    return {"value": frames * cfg.antenna_samples_per_frame / dt, "unit": UNIT, "cores": n_threads, "kind": "port",
+            "sample": f"{frames} frames of {cfg.name} ({F0} frames x {reps} passes, {dt:.1f} s), oracle/cpuls_oracle.c "
+                      f"-O3 -march=native, FFT = oracle/fft_shim.c (FFTW3 absent), frames split over {n_threads} threads"}
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU path (oracle port, all host threads), same metric/config"""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle_py
+    import ofdm_b200 as m
+
+    oracle_py.build(ref=False)
+    n_threads = os.cpu_count() or 1
+    A, N, C, S = cfg.n_ant, cfg.fft_size, cfg.cp_len, cfg.n_sym
+    pilot = m.synth.make_pilot(cfg.K, cfg.seed)
+    rng = np.random.default_rng(11)
+    # one step = a bounded sample: one frame per host thread (whole run stays within minutes)
+    F = max(1, min(n_threads, max(1, int(2e9 // cfg.rx_bytes_per_frame))))
+    rx = rng.standard_normal((F, S, A, N + C, 2), dtype=np.float32).view(np.complex64)[..., 0]
+    for _ in range(args.warmup):
+        oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
+    dt = time.perf_counter() - t0
+    value = args.steps * F * cfg.antenna_samples_per_frame / dt
+    sample = (f"{F} frames of {cfg.name} per step on {n_threads} host threads; oracle port of cpuLS.hpp "
+              f"(reference needs compile-time dims and FFTW3, see DESIGN.md)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, F, None),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, frames, e2e_frames):
+    return {"workload": f"{cfg.name}: {cfg.fft_size}-pt FFT, CP {cfg.cp_len}, {cfg.n_ant} antennas, 1 pilot + "
+                        f"{cfg.n_sym - 1} data symbols, {1 << cfg.qam_bits}-QAM",
+            "frames_per_step_per_gpu": frames, "e2e_frames_per_step_per_gpu": e2e_frames,
+            "input_bytes_per_step_per_gpu": frames * cfg.rx_bytes_per_frame,
+            "l2_policy": "inputs larger than L2 (each step streams its whole batch from HBM once)",
+            "note": "10k-frame batch processed as resident chunks; one chunk = one step"}
+
+
+def main():
+    args = parse_args()
+    import ofdm_b200 as m
+
+    cfg = m.CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    import numpy as np
+    import torch
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the receiver has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    F = args.frames or DEFAULT_FRAMES[cfg.name]
+    Fe = args.e2e_frames or DEFAULT_E2E_FRAMES[cfg.name]
+    # frames are independent: rank r owns global frames [r*F, (r+1)*F) of every step (no collective on the path)
+    rx, pilot_asc, src = m.synth.make_frames_torch(F, cfg, dev, seed=cfg.seed + 1000 * rank, chunk=8)
+    rx_f = torch.view_as_real(rx)
+    comb = torch.empty((F, cfg.n_sym - 1, cfg.K, 2), device=dev, dtype=torch.float32)
+    bits = torch.empty((F, cfg.n_sym - 1, cfg.bits_row_bytes), device=dev, dtype=torch.uint8)
+    rcv = m.LsMrcReceiver.from_config(cfg, max_frames=max(1, min(Fe, 8)), device=local, n_lanes=3)
+    rcv.set_pilot(pilot_asc)
+    stream = torch.cuda.current_stream(dev)
+    rcv.set_stream(stream.cuda_stream)
+
+    def step():
+        rcv.demod_frames_device(rx_f, F, comb, bits)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- correctness gate on this very batch: decoded bits vs the transmitted bits
+    step()
+    torch.cuda.synchronize(dev)
+    want = torch.from_numpy(m.synth.pack_bits_rows(src[:2].cpu().numpy(), cfg.qam_bits))
+    got = bits[:2].cpu()
+    bit_errors = int(np.unpackbits((got ^ want).numpy()).sum())
+    ber = bit_errors / float(want.numel() * 8)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # samples through warm-up and the timed region; idle samples are filtered by power
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = rcv.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = rcv.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * F * args.steps * cfg.antenna_samples_per_frame / (ms_max * 1e-3)
+
+    # ---- per-kernel pass: CUDA-event duration of the dominant (data) kernel
+    rcv.set_timing(True)
+    p_ms, d_ms = [], []
+    for _ in range(max(3, min(args.steps, 10))):
+        step()
+        a, b = rcv.last_kernel_ms()
+        p_ms.append(a)
+        d_ms.append(b)
+    rcv.set_timing(False)
+    data_ms = statistics.mean(d_ms)
+    pilot_ms = statistics.mean(p_ms)
+    A, N, S, K = cfg.n_ant, cfg.fft_size, cfg.n_sym, cfg.K
+    data_bytes_per_frame = 8 * A * (S - 1) * N + 8 * (S - 1) * K + (S - 1) * cfg.bits_row_bytes
+    peak, peak_src = measured_peak_gbs()
+    achieved = F * data_bytes_per_frame / (data_ms * 1e-3) / 1e9
+    tpf = profile_traffic_per_frame(cfg.name)
+    roofline = {"bound": "hbm", "kernel": "lsmrc_kernel<MODE_DATA> (FFT + MRC + demap)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (tpf * F) if tpf else None, "algorithmic_bytes_per_launch": F * data_bytes_per_frame,
+                "kernel_ms": data_ms, "pilot_kernel_ms": pilot_ms, "kernel_share_of_step": data_ms / (data_ms + pilot_ms),
+                "whole_path_achieved": F * cfg.algorithmic_bytes_per_frame / ((data_ms + pilot_ms) * 1e-3) / 1e9}
+
+    # ---- e2e: host buffers through the public call, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_rx = rcv.pinned_array((Fe, cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len), np.complex64)
+        h_rx[...] = rx[:Fe].cpu().numpy() if Fe <= F else np.resize(rx.cpu().numpy(), h_rx.shape)
+        h_comb = rcv.pinned_array((Fe, cfg.n_sym - 1, cfg.K), np.complex64)
+        h_bits = rcv.pinned_array((Fe, cfg.n_sym - 1, cfg.bits_row_bytes), np.uint8)
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            rcv.demod_frames_host(h_rx, Fe, h_comb, h_bits)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            rcv.demod_frames_host(h_rx, Fe, h_comb, h_bits)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e_err = int(np.unpackbits(h_bits[:1] ^ got[:1].numpy()).sum()) if Fe >= 1 else 0
+        e2e = {"value": world * Fe * n_e2e * cfg.antenna_samples_per_frame / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_rx.nbytes), "d2h_bytes_per_step": int(h_comb.nbytes + h_bits.nbytes),
+               "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e, "api": "lsmrc_demod_frames_host (pinned host buffers, 3 lanes)",
+               "h2d_gbs": world * h_rx.nbytes * n_e2e / dt / 1e9, "bit_mismatch_vs_device_path": e2e_err}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cfg, os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(cfg, F, Fe), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clocks, "plan": rcv.describe_plan(),
+                "parity": {"bit_errors_vs_source": bit_errors, "ber": ber, "frames_checked": 2}}
+        print(json.dumps(line), flush=True)
+    rcv.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
