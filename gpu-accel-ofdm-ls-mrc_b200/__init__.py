@@ -6,4 +6,4 @@ This Python package is a thin ctypes binding of the same ABI for tests and bench
 """
 from .configs import CONFIGS, RxConfig  # noqa: F401
 from .binding import ABI, LsMrcReceiver, LsmrcError, load_library  # noqa: F401
-from . import build, synth  # noqa: F401
+from . import build, sharding, synth  # noqa: F401

@@ -34,6 +34,7 @@ ABI = {
     "lsmrc_first_vector": (c_int, [c_void_p, c_void_p, c_int]),
     "lsmrc_demod_one_symbol": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "lsmrc_get_channel": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lsmrc_get_channel_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "lsmrc_ring_submit_frame": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "lsmrc_ring_submit_split": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "lsmrc_ring_wait": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),

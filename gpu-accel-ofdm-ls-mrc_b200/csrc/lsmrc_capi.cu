@@ -740,6 +740,20 @@ int lsmrc_get_channel(lsmrc_handle h, void* h_hconj, void* h_hsqrd)
     return LSMRC_OK;
 }
 
+int lsmrc_get_channel_device(lsmrc_handle h, void* d_hconj, void* d_hsqrd)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    if (!h->have_channel) return fail(h, LSMRC_ERR_STATE, "no channel estimate yet");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->own_stream;
+    if (d_hconj)
+        CK(h, cudaMemcpyAsync(d_hconj, h->d_one_hconj, (size_t)h->cfg.n_ant * h->K * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    if (d_hsqrd)
+        CK(h, cudaMemcpyAsync(d_hsqrd, h->one_ch.hsqrd, (size_t)h->K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(h, cudaStreamSynchronize(st));
+    return LSMRC_OK;
+}
+
 // ---- ring lanes -----------------------------------------------------------------------
 
 static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L)

@@ -60,13 +60,13 @@ def pack_bits_rows(idx: np.ndarray, qam_bits: int) -> np.ndarray:
 
 
 def make_frames(n_frames, n_ant, fft_size, cp_len, n_sym, qam_bits, snr_db=None, seed=0,
-                channel="rayleigh"):
+                channel="rayleigh", pilot_asc=None):
     """Returns dict(rx [F,S,A,N+C] c64, pilot_asc [K] c64, src_idx [F,S-1,K] u8 (ascending
     frequency), h_true [F,A,K] c128 (bin order))."""
     F, A, N, C, S = n_frames, n_ant, fft_size, cp_len, n_sym
     K = N - 1
     rng = np.random.default_rng(seed)
-    pilot_asc = make_pilot(K, seed)
+    pilot_asc = make_pilot(K, seed) if pilot_asc is None else np.asarray(pilot_asc, np.complex64)
     src_idx = rng.integers(0, 1 << qam_bits, size=(F, S - 1, K), dtype=np.uint8)
     data_asc = qam_map_indices(src_idx, qam_bits)
     tx_bin = np.zeros((F, S, N), np.complex128)

@@ -109,6 +109,9 @@ int lsmrc_first_vector(lsmrc_handle h, const void *rx_sym, int on_device);
 int lsmrc_demod_one_symbol(lsmrc_handle h, const void *rx_sym, int on_device,
                            void *h_combined /* K complex64, host */, void *h_bits /* row bytes, host, may be NULL */);
 int lsmrc_get_channel(lsmrc_handle h, void *h_hconj /* [A][K] */, void *h_hsqrd /* [K] */);
+/* same, into caller-owned DEVICE buffers: the dH / Hsqrd arguments of gpuLS::firstVector
+ * (gpuLS.cu:351), which the reference leaves filled for the caller.  Either may be NULL. */
+int lsmrc_get_channel_device(lsmrc_handle h, void *d_hconj /* [A][K] */, void *d_hsqrd /* [K] */);
 
 /* ---- streaming ingest from a pinned ring (replaces ShMemSymBuff::readNextSymbolCUDA /
  *      readLastSymbolCUDA, ShMemSymBuff_gpu.hpp:373-445, plus the demod calls that follow

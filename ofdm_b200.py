@@ -23,4 +23,5 @@ LsmrcError = pkg.LsmrcError
 load_library = pkg.load_library
 synth = pkg.synth
 build = pkg.build
+sharding = pkg.sharding
 ABI = pkg.ABI

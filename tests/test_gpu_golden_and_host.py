@@ -1,0 +1,115 @@
+"""More -m gpu parity: the committed golden fixtures (outputs of the reference's own CPU code),
+the C++ host programs that keep the reference's entry points (ring feeder -> ring -> gpuLS_main /
+stream_main), and size-independent properties at BASELINE.json's full dimensions."""
+import glob
+import os
+import subprocess
+import uuid
+
+import numpy as np
+import pytest
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "gpu-accel-ofdm-ls-mrc_b200", "host")
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_path_matches_reference_golden(ofdm, path):
+    g = np.load(path)
+    A, N, C, S, b, F = (int(v) for v in g["dims"])
+    with ofdm.LsMrcReceiver(A, N, C, S, b, max_frames=2, n_lanes=2) as rx:
+        if bool(g["fallback_pilot"]):
+            assert rx.set_pilot_file("/nonexistent/Pilots.dat") == 1   # cpuLS.hpp:85-88 fallback
+        else:
+            rx.set_pilot(g["pilot_asc"])
+        got = rx.demod_numpy(g["rx"])
+    assert_close(got["hconj"], g["hconj"], "Hconj vs reference build")
+    assert_close(got["hsqrd"], g["hsqrd"], "sum|H|^2 vs reference build")
+    assert_close(got["combined"], g["combined"], "combined vs reference build")
+    assert np.array_equal(got["bits"], g["bits"])
+
+
+@pytest.fixture(scope="module")
+def host_bins(ofdm):
+    ofdm.load_library()
+    subprocess.run(["make", "-C", HOST, "--no-print-directory"], check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(HOST, "bin")
+
+
+def _run_ring(host_bins, tmp_path, consumer, extra, d, A, N, C, S, b, F, ring):
+    shm = "/lsmrc_" + uuid.uuid4().hex[:8]
+    rx_file = tmp_path / "rx.bin"
+    d["rx"].tofile(rx_file)
+    pil = tmp_path / "Pilots.dat"
+    d["pilot_asc"].tofile(pil)
+    dims = ["--rows", str(A), "--cols", str(N), "--prefix", str(C), "--syms", str(S), "--ring", str(ring), "--shm", shm]
+    feeder = subprocess.Popen([os.path.join(host_bins, "ring_feeder"), "--file", str(rx_file), "--frames", str(F)] + dims)
+    try:
+        r = subprocess.run([os.path.join(host_bins, consumer), "--qam", str(b), "--frames", str(F), "--pilots", str(pil)] + dims + extra,
+                           cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    finally:
+        feeder.wait(timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    K = N - 1
+    comb = np.fromfile(tmp_path / "Output_gpu.dat", np.complex64).reshape(F, S - 1, K)
+    bits = np.fromfile(tmp_path / "Bits_gpu.dat", np.uint8).reshape(F, S - 1, -1)
+    return comb, bits, r.stdout
+
+
+@pytest.mark.parametrize("consumer,extra", [("gpuLS_main", []), ("gpuLS_main", ["--frame-mode"]), ("stream_main", [])])
+def test_ring_fed_cpp_consumers_match_oracle(ofdm, oracle, host_bins, tmp_path, consumer, extra):
+    A, N, C, S, b, F = 4, 64, 16, 16, 2, 7            # config c1 through the ring
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=10.0, seed=1235)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    ring = S + 1 if (consumer == "gpuLS_main" and not extra) else 4 * S + 1
+    comb, bits, _ = _run_ring(host_bins, tmp_path, consumer, extra, d, A, N, C, S, b, F, ring)
+    assert_close(comb, ref["combined"], f"{consumer} combined")
+    assert np.array_equal(bits, ref["bits"])
+
+
+def test_stream_main_config3_dims(ofdm, oracle, host_bins, tmp_path):
+    A, N, C, S, b, F = 16, 2048, 144, 14, 4, 5        # config c3 shape with fewer antennas
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=15.0, seed=1237)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    comb, bits, out = _run_ring(host_bins, tmp_path, "stream_main", [], d, A, N, C, S, b, F, 4 * S + 1)
+    assert_close(comb, ref["combined"], "stream_main combined")
+    assert np.array_equal(bits, ref["bits"])
+    assert "antenna_samples_per_s" in out
+
+
+# ---- full BASELINE dimensions: properties that do not need the (slow) oracle --------------------
+@pytest.mark.parametrize("name,frames", [("c2", 3), ("c3", 2), ("c4", 1), ("c5", 4)])
+def test_full_size_round_trip_and_linearity(ofdm, name, frames):
+    import torch
+
+    cfg = ofdm.CONFIGS[name]
+    dev = torch.device("cuda:0")
+    rx, pilot_asc, src = ofdm.synth.make_frames_torch(frames, cfg, dev, chunk=1)
+    K, S = cfg.K, cfg.n_sym
+    comb = torch.empty((frames, S - 1, K, 2), device=dev)
+    bits = torch.empty((frames, S - 1, cfg.bits_row_bytes), device=dev, dtype=torch.uint8)
+    hc = torch.empty((frames, cfg.n_ant, K, 2), device=dev)
+    hs = torch.empty((frames, K), device=dev)
+    with ofdm.LsMrcReceiver.from_config(cfg) as r:
+        r.set_pilot(pilot_asc)
+        r.demod_frames_device(torch.view_as_real(rx), frames, comb, bits, hc, hs)
+        r.sync()
+        # encode -> channel -> decode round trip: decoded bits are the transmitted bits
+        want = ofdm.synth.pack_bits_rows(src.cpu().numpy(), cfg.qam_bits)
+        assert np.array_equal(bits.cpu().numpy(), want)
+        # sum|H|^2 is the energy of the stored estimate
+        e = (hc ** 2).sum(dim=(1, 3))
+        assert torch.allclose(e, hs, rtol=1e-4)
+        # linearity in the data symbols: scaling every data symbol by g scales the combined output by g,
+        # the channel estimate (pilot symbol untouched) stays put
+        g = 0.5
+        rx2 = rx.clone()
+        rx2[:, 1:] *= g
+        comb2 = torch.empty_like(comb)
+        r.demod_frames_device(torch.view_as_real(rx2), frames, comb2, None)
+        r.sync()
+        assert torch.allclose(comb2, comb * g, rtol=1e-5, atol=1e-6)
