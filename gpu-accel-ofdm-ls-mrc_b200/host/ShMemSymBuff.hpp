@@ -132,7 +132,10 @@ class ShMemSymBuff {
         int w = load(kWrite);
         if (w < 0) w = 0;
         const int nxt = next(w);
-        while (nxt == load(kRead)) relax();
+        while (nxt == load(kRead)) {
+            if (load(kSize) == -1) return;  // the reader has gone away: drop the symbol instead of spinning
+            relax();
+        }
         std::memcpy(slot(w), Yf, slotBytes());
         store(kWrite, nxt);
     }

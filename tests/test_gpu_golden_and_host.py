@@ -51,9 +51,13 @@ def _run_ring(host_bins, tmp_path, consumer, extra, d, A, N, C, S, b, F, ring):
     try:
         r = subprocess.run([os.path.join(host_bins, consumer), "--qam", str(b), "--frames", str(F), "--pilots", str(pil)] + dims + extra,
                            cwd=tmp_path, capture_output=True, text=True, timeout=120)
-    finally:
+        assert r.returncode == 0, r.stdout + r.stderr
         feeder.wait(timeout=60)
-    assert r.returncode == 0, r.stdout + r.stderr
+    finally:
+        if feeder.poll() is None:
+            feeder.kill()
+        if os.path.exists("/dev/shm" + shm):
+            os.unlink("/dev/shm" + shm)
     K = N - 1
     comb = np.fromfile(tmp_path / "Output_gpu.dat", np.complex64).reshape(F, S - 1, K)
     bits = np.fromfile(tmp_path / "Bits_gpu.dat", np.uint8).reshape(F, S - 1, -1)
