@@ -114,7 +114,7 @@ PlanOps make_ops()
 #define LSMRC_1024_MINB 3
 #endif
 #ifndef LSMRC_1024_REGPF
-#define LSMRC_1024_REGPF false
+#define LSMRC_1024_REGPF 0
 #endif
 #ifndef LSMRC_1024_XL1
 #define LSMRC_1024_XL1 false

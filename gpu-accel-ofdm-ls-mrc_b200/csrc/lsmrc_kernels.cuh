@@ -35,6 +35,10 @@
 
 #include "fft_radix.cuh"
 
+#ifndef LSMRC_TW_CHUNK
+#define LSMRC_TW_CHUNK 4
+#endif
+
 namespace lsmrc {
 
 enum { MODE_PILOT = 0, MODE_DATA = 1 };
@@ -71,16 +75,18 @@ struct KernelParams {
     const float2* twiddles;  // plan table: tw1 [(P-1)][T] then tw2 [(R2-1)][R3]
 };
 
-template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, bool REG_PF_ = false, bool X_L1_ = false, bool H_RING_ = false>
+template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false>
 struct Plan {
-    // REG_PF: data kernel loads row a+1 into registers while row a is in stage 2/3 + MRC
-    static constexpr bool REG_PF = REG_PF_;
+    // REG_PF: data kernel loads row a+1 into registers while row a is still being processed:
+    // 1 = all loads right after stage 1, 2 = one load per MRC accumulation (as registers free up)
+    static constexpr int REG_PF = REG_PF_;
     // X_L1: prefetch the antenna-samples into L1 (and load them with L1 allocation) instead of L2
     static constexpr bool X_L1 = X_L1_;
     // H_RING: the TEAMS teams of a CTA work on TEAMS data symbols of ONE frame and share each
     // Hconj row through a shared-memory ring filled by bulk async copies (TMA) on mbarriers
     static constexpr bool H_RING = H_RING_;
     static constexpr int H_STAGES = 3;
+    static constexpr int TW_CHUNK = (P_ >= 8) ? LSMRC_TW_CHUNK : P_;  // inter-stage twiddles fetched this many at a time
     static constexpr int HRING = H_RING_ ? H_STAGES * N_ : 0;  // complex elements
     // PF_X: rows ahead whose antenna-samples are prefetched into L2; PF_H: rows ahead whose
     // Hconj row is prefetched into L1 (0 = off)
@@ -106,11 +112,21 @@ struct Plan {
     static_assert(T <= 32 || TEAMS <= 15, "named barriers 1..15");
 };
 
+__device__ __forceinline__ uint32_t smem_u32_c(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // streaming 64-bit load of one antenna-sample: read once, keep it out of L1
 __device__ __forceinline__ float2 ld_stream(const float2* p)
 {
     float2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+// shared-memory 64-bit load the compiler may not move or merge (used to pin prefetch distance)
+__device__ __forceinline__ float2 lds_volatile(const float2* p)
+{
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(smem_u32_c(p)));
     return r;
 }
 
@@ -235,11 +251,33 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
 {
     constexpr int P = PL::P, T = PL::T, ROW = PL::ROW, R2 = PL::R2, R3 = PL::R3;
     fft_reg<P>(v);
+    // Inter-stage twiddles W_N^(t*k1) come from the shared table.  They are fetched in chunks of
+    // TWC, one chunk ahead of the multiplies that use them, through volatile loads fenced with
+    // compiler barriers: left to itself ptxas (168-register budget) sinks every twiddle load to
+    // just before its multiply and exposes the ~30-cycle shared-memory latency 31 times per row.
+    constexpr int TWC = PL::TW_CHUNK;
+    static_assert(P % TWC == 0, "chunk must divide P");
+    float2 twa[TWC], twb[TWC];
 #pragma unroll
-    for (int k1 = 0; k1 < P; ++k1) {
-        float2 val = v[brev<P>(k1)];
-        if (k1 > 0) val = cmul(val, s_tw1[(k1 - 1) * T + t]);
-        tile[k1 * ROW + t] = val;
+    for (int j = 0; j < TWC; ++j) twa[j] = (j == 0) ? make_float2(1.f, 0.f) : lds_volatile(s_tw1 + (j - 1) * T + t);
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < P / TWC; ++c) {
+        if (c + 1 < P / TWC) {
+#pragma unroll
+            for (int j = 0; j < TWC; ++j) twb[j] = lds_volatile(s_tw1 + ((c + 1) * TWC + j - 1) * T + t);
+        }
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < TWC; ++j) {
+            const int k1 = c * TWC + j;
+            float2 val = v[brev<P>(k1)];
+            if (k1 > 0) val = cmul(val, twa[j]);
+            tile[k1 * ROW + t] = val;
+        }
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < TWC; ++j) twa[j] = twb[j];
     }
     if (x_next != nullptr) row_load<PL>(v, x_next, t);
     team_sync<PL>(team);
@@ -454,7 +492,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             const int st = a % PL::H_STAGES;
             const float2* h_src = PL::H_RING ? (s_hring + st * N) : hw_row;
             bool h_ready = !PL::H_RING;
-            row_fft<PL>(v, x_next, tile, s_tw1, s_tw2, t, team,
+            row_fft<PL>(v, PL::REG_PF == 1 ? x_next : nullptr, tile, s_tw1, s_tw2, t, team,
                         [&](int sl, int bin, float2 y) {
                             // cpuLS.hpp:187-208: acc += Y * Hconj
                             if constexpr (PL::H_RING) {
@@ -463,6 +501,11 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                     h_ready = true;
                                 }
                                 acc[sl] = cmac(acc[sl], h_src[bin], y);
+                                if constexpr (PL::REG_PF == 2) {
+                                    // the register pair that held this row's sample sl is free: refill it
+                                    // with the next row's sample so its latency hides behind the rest of the MRC
+                                    if (x_next != nullptr) v[sl] = ld_stream(x_next + sl * T + t);
+                                }
                             } else {
 #ifdef LSMRC_FAKE_H  // experiment only
                                 float2 h = make_float2(1.f + sl, 0.5f);

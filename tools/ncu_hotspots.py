@@ -5,10 +5,11 @@ import sys
 
 rep, sec = sys.argv[1], int(sys.argv[2])
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--launch-skip", str(sec),
+                      "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
-block = rows[starts[sec]:starts[sec + 1]]
+block = rows[starts[0]:starts[1]]
 print(block[0][1][:120])
 hdr = block[1]
 data = [r for r in block[2:] if len(r) == len(hdr)]
