@@ -52,7 +52,7 @@ def parse_args():
 
 
 # frames per step per GPU: large enough that one step's input exceeds the 126 MB L2 many times over
-DEFAULT_FRAMES = {"c1": 65536, "c2": 64, "c3": 96, "c4": 24, "c5": 16384}
+DEFAULT_FRAMES = {"c1": 65536, "c2": 256, "c3": 192, "c4": 48, "c5": 16384}
 DEFAULT_E2E_FRAMES = {"c1": 16384, "c2": 16, "c3": 32, "c4": 8, "c5": 8192}
 
 

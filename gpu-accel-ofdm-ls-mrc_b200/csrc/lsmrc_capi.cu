@@ -50,10 +50,15 @@ void fill_twiddles_impl(float2* tw)
             }
 }
 
+// the pilot kernel keeps the pilot, 1/|X|^2 and the energy partials of its P bins in registers on
+// top of the FFT working set: give the 32-point plans a 255-register budget there
+template <class PL, int MINB>
+constexpr int pilot_minb() { return PL::P >= 32 ? (MINB < 2 ? MINB : 2) : MINB; }
+
 template <class PL, int MINB>
 cudaError_t prepare_impl()
 {
-    cudaError_t e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_PILOT, MINB>,
+    cudaError_t e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_DATA, MINB>,
@@ -64,7 +69,7 @@ template <class PL, int MINB>
 cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st)
 {
     if (mode == MODE_PILOT) {
-        lsmrc_kernel<PL, MODE_PILOT, MINB><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+        lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
         unsigned grid;
         if (PL::H_RING) {

@@ -33,8 +33,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fft_radix.cuh"
 
+#ifndef LSMRC_H_STAGES
+#define LSMRC_H_STAGES 3
+#endif
 #ifndef LSMRC_TW_CHUNK
 #define LSMRC_TW_CHUNK 4
 #endif
@@ -78,14 +83,18 @@ struct KernelParams {
 template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false>
 struct Plan {
     // REG_PF: data kernel loads row a+1 into registers while row a is still being processed:
-    // 1 = all loads right after stage 1, 2 = one load per MRC accumulation (as registers free up)
+    // 1 = all loads right after stage 1, 2 = one load per MRC accumulation (as registers free up),
+    // 3 = the even-indexed half during the second half of the MRC, the odd half at the top of the
+    //     next row: the first four DIT layers of the even half need no odd sample, so they run
+    //     while the odd loads are still in flight
     static constexpr int REG_PF = REG_PF_;
     // X_L1: prefetch the antenna-samples into L1 (and load them with L1 allocation) instead of L2
     static constexpr bool X_L1 = X_L1_;
     // H_RING: the TEAMS teams of a CTA work on TEAMS data symbols of ONE frame and share each
     // Hconj row through a shared-memory ring filled by bulk async copies (TMA) on mbarriers
     static constexpr bool H_RING = H_RING_;
-    static constexpr int H_STAGES = 3;
+    static constexpr int H_STAGES = LSMRC_H_STAGES;   // ring depth
+    static constexpr int H_AHEAD = LSMRC_H_STAGES - 2; // rows kept in flight ahead of the row being consumed
     static constexpr int TW_CHUNK = (P_ >= 8) ? LSMRC_TW_CHUNK : P_;  // inter-stage twiddles fetched this many at a time
     static constexpr int HRING = H_RING_ ? H_STAGES * N_ : 0;  // complex elements
     // PF_X: rows ahead whose antenna-samples are prefetched into L2; PF_H: rows ahead whose
@@ -348,14 +357,14 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
         float e[P];
         float2 xp[P];   // pilot value per owned bin
-        float xden[P];  // |X|^2, hoisted: cpuLS.hpp:240-241 recomputes it per element
+        float xden[P];  // 1/|X|^2, hoisted: cpuLS.hpp:240-241 divides by |X|^2 per element (<= 1 ulp apart)
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
             const int i = sl / PL::RL, j = sl % PL::RL;
             const int bin = t + T * i + (N / PL::RL) * j;
             e[sl] = 0.f;
             xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
-            xden[sl] = xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y;
+            xden[sl] = 1.0f / (xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y);
         }
         const int per_iter = p.n_groups * PL::TEAMS;
         const int n_iter = (p.n_ant + per_iter - 1) / per_iter;
@@ -372,8 +381,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                         [&](int sl, int bin, float2 z) {
                             // LS estimate, naive complex division of cpuLS.hpp:233-244, then conj (:303-307)
                             const float2 X = xp[sl];
-                            const float re = (z.x * X.x + z.y * X.y) / xden[sl];
-                            const float im = (z.y * X.x - z.x * X.y) / xden[sl];
+                            const float re = (z.x * X.x + z.y * X.y) * xden[sl];
+                            const float im = (z.y * X.x - z.x * X.y) * xden[sl];
                             if (a_ok) {
                                 const float2 hc = (bin > 0) ? make_float2(re, -im) : make_float2(0.f, 0.f);
                                 hw_row[bin] = hc;
@@ -444,10 +453,10 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) acc[sl] = make_float2(0.f, 0.f);
 
-        // Hconj ring: stage r%3 holds row r; full[] completes on the copy's bytes, empty[] when
-        // every team has consumed the row.  Thread 0 keeps one row in flight ahead of the row
-        // being consumed; a stage is only refilled two rows after its last use, so the producer
-        // practically never waits on a straggling team.
+        // Hconj ring: stage r%H_STAGES holds row r; full[] completes on the copy's bytes, empty[]
+        // when every team has consumed the row.  Thread 0 keeps H_AHEAD rows in flight ahead of
+        // the row being consumed; a stage is only refilled two rows after its last use, so the
+        // producer practically never waits on a straggling team.
         __shared__ __align__(8) uint64_t bar_full[PL::H_STAGES], bar_empty[PL::H_STAGES];
         constexpr uint32_t ROW_BYTES = N * sizeof(float2);
         if constexpr (PL::H_RING) {
@@ -460,18 +469,24 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                mbar_expect_tx(&bar_full[0], ROW_BYTES);
-                bulk_g2s(s_hring, hw_frame, ROW_BYTES, &bar_full[0]);
+                for (int r = 0; r < PL::H_AHEAD && r < p.n_ant; ++r) {
+                    mbar_expect_tx(&bar_full[r], ROW_BYTES);
+                    bulk_g2s(s_hring + r * N, hw_frame + (long long)r * N, ROW_BYTES, &bar_full[r]);
+                }
             }
         }
 
         float2 v[P];
-        if (PL::REG_PF) row_load<PL>(v, x0, t);
+        if (PL::REG_PF == 1 || PL::REG_PF == 2) row_load<PL>(v, x0, t);
+        if constexpr (PL::REG_PF == 3) {
+#pragma unroll
+            for (int n1 = 0; n1 < P; n1 += 2) v[n1] = ld_stream(x0 + n1 * T + t);
+        }
         for (int a = 0; a < p.n_ant; ++a) {
             float2* tile = my_tiles + (PL::NBUF == 2 ? (a & 1) * PL::TILE : 0);
             const float2* hw_row = hw_frame + (long long)a * N;
             if constexpr (PL::H_RING) {
-                const int r = a + 1;
+                const int r = a + PL::H_AHEAD;
                 if (threadIdx.x == 0 && r < p.n_ant) {
                     const int sr = r % PL::H_STAGES, use = r / PL::H_STAGES;
                     if (use > 0) mbar_wait(&bar_empty[sr], (uint32_t)((use - 1) & 1));
@@ -481,10 +496,16 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                 __syncwarp();
             }
             const float2* x_next = nullptr;
-            if (PL::REG_PF) {
+            if (PL::REG_PF != 0) {
                 if (a + 1 < p.n_ant) x_next = x0 + (long long)(a + 1) * p.ant_stride;
-            } else {
+            }
+            if (PL::REG_PF == 0) {
                 row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
+            }
+            if constexpr (PL::REG_PF == 3) {
+                const float2* xr = x0 + (long long)a * p.ant_stride;
+#pragma unroll
+                for (int n1 = 1; n1 < P; n1 += 2) v[n1] = ld_stream(xr + n1 * T + t);
             }
             if (PF_X > 0 && a + PF_X < p.n_ant)
                 prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X) * p.ant_stride, N, t);
@@ -505,6 +526,10 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                     // the register pair that held this row's sample sl is free: refill it
                                     // with the next row's sample so its latency hides behind the rest of the MRC
                                     if (x_next != nullptr) v[sl] = ld_stream(x_next + sl * T + t);
+                                }
+                                if constexpr (PL::REG_PF == 3) {
+                                    if (sl >= P / 2 && x_next != nullptr)
+                                        v[2 * (sl - P / 2)] = ld_stream(x_next + 2 * (sl - P / 2) * T + t);
                                 }
                             } else {
 #ifdef LSMRC_FAKE_H  // experiment only
@@ -543,17 +568,23 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         if (p.bits != nullptr) {
             team_sync<PL>(team);
             uint8_t* bits_row = p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes;
-            const int b = p.qam_bits;
-            for (int byte = t; byte < p.bits_row_bytes; byte += T) {
-                unsigned v8 = 0;
+            // one output byte per thread and step; the symbol/bit split uses a compile-time b
+            auto pack = [&](auto bconst) {
+                constexpr int b = decltype(bconst)::value;
+                for (int byte = t; byte < p.bits_row_bytes; byte += T) {
+                    unsigned v8 = 0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int pos = byte * 8 + q;
-                    const int sym = pos / b, bit = pos - sym * b;
-                    if (sym < K) v8 |= ((s_idx[sym] >> bit) & 1u) << q;
+                    for (int q = 0; q < 8; ++q) {
+                        const int pos = byte * 8 + q;
+                        const int sym = pos / b, bit = pos - sym * b;
+                        if (sym < K) v8 |= ((s_idx[sym] >> bit) & 1u) << q;
+                    }
+                    if (valid) bits_row[byte] = (uint8_t)v8;
                 }
-                if (valid) bits_row[byte] = (uint8_t)v8;
-            }
+            };
+            if (p.qam_bits == 2) pack(std::integral_constant<int, 2>{});
+            else if (p.qam_bits == 4) pack(std::integral_constant<int, 4>{});
+            else pack(std::integral_constant<int, 6>{});
         }
     }
 }
