@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c5 latency and other-config legs")
     return ap.parse_args()
 
 
@@ -211,6 +212,69 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def latency_leg(m, dev_index, n_launch=3000):
+    """BASELINE config c5: one frame per launch (64-pt FFT, 16 antennas), p50/p99 per-frame latency,
+    host clock around submit + sync of the two kernels (device-resident frame)."""
+    import numpy as np
+    import torch
+
+    cfg = m.CONFIGS["c5"]
+    dev = torch.device("cuda", dev_index)
+    rx, pilot_asc, _ = m.synth.make_frames_torch(1, cfg, dev)
+    comb = torch.empty((1, cfg.n_sym - 1, cfg.K, 2), device=dev)
+    bits = torch.empty((1, cfg.n_sym - 1, cfg.bits_row_bytes), device=dev, dtype=torch.uint8)
+    rxf = torch.view_as_real(rx)
+    with m.LsMrcReceiver.from_config(cfg, device=dev_index) as r:
+        r.set_pilot(pilot_asc)
+        for _ in range(200):
+            r.demod_frames_device(rxf, 1, comb, bits)
+        r.sync()
+        lat = np.empty(n_launch)
+        for i in range(n_launch):
+            t0 = time.perf_counter()
+            r.demod_frames_device(rxf, 1, comb, bits)
+            r.sync()
+            lat[i] = time.perf_counter() - t0
+        r.set_timing(True)
+        dev_us = []
+        for _ in range(200):
+            r.demod_frames_device(rxf, 1, comb, bits)
+            a, b = r.last_kernel_ms()
+            dev_us.append(1e3 * (a + b))
+    return {"workload": "c5: 64-pt FFT, 16 antennas, 16 symbols, QPSK, one frame per launch", "launches": n_launch,
+            "p50_us": float(np.percentile(lat, 50) * 1e6), "p99_us": float(np.percentile(lat, 99) * 1e6),
+            "mean_us": float(lat.mean() * 1e6), "device_us_p50": float(np.percentile(dev_us, 50)),
+            "what": "host steady clock around lsmrc_demod_frames_device + lsmrc_sync (2 kernel launches per frame)"}
+
+
+def other_configs_leg(m, dev_index, peak):
+    """kernel-time throughput of the remaining BASELINE dimension sets (parity for them is in tests/)"""
+    import torch
+
+    out = {}
+    dev = torch.device("cuda", dev_index)
+    for name, frames in (("c1", 8192), ("c3", 64), ("c4", 16)):
+        cfg = m.CONFIGS[name]
+        rx = torch.randn((frames, cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len, 2), device=dev)
+        comb = torch.empty((frames, cfg.n_sym - 1, cfg.K, 2), device=dev)
+        bits = torch.empty((frames, cfg.n_sym - 1, cfg.bits_row_bytes), device=dev, dtype=torch.uint8)
+        with m.LsMrcReceiver.from_config(cfg, device=dev_index) as r:
+            r.set_pilot(m.synth.make_pilot(cfg.K, 1))
+            r.set_timing(True)
+            ms = []
+            for _ in range(6):
+                r.demod_frames_device(rx, frames, comb, bits)
+                a, b = r.last_kernel_ms()
+                ms.append(a + b)
+            t = statistics.median(ms[2:])
+            gbs = frames * cfg.algorithmic_bytes_per_frame / (t * 1e-3) / 1e9
+            out[name] = {"frames": frames, "ms": t, "antenna_samples_per_s": frames * cfg.antenna_samples_per_frame / (t * 1e-3),
+                         "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "plan": r.describe_plan()}
+        del rx, comb, bits
+        torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(cfg, frames, e2e_frames):
     return {"workload": f"{cfg.name}: {cfg.fft_size}-pt FFT, CP {cfg.cp_len}, {cfg.n_ant} antennas, 1 pilot + "
                         f"{cfg.n_sym - 1} data symbols, {1 << cfg.qam_bits}-QAM",
@@ -345,12 +409,20 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(cfg, os.cpu_count() or 1)
 
+    latency = others = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del rx, rx_f, comb, bits
+        torch.cuda.empty_cache()
+        latency = latency_leg(m, local)
+        others = other_configs_leg(m, local, peak)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, F, Fe), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches, "clocks": clocks, "plan": rcv.describe_plan(),
+                "gpu_launches": launches, "clocks": clocks, "plan": rcv.describe_plan(), "latency": latency,
+                "other_configs": others,
                 "parity": {"bit_errors_vs_source": bit_errors, "ber": ber, "frames_checked": 2}}
         print(json.dumps(line), flush=True)
     rcv.close()

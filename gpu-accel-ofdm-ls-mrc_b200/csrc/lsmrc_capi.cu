@@ -29,8 +29,8 @@ struct PlanOps {
     int N, P, R2, R3, teams, threads, twn, minb;
     size_t smem;
     void (*fill_twiddles)(float2*);
-    cudaError_t (*prepare)();
-    cudaError_t (*launch)(int mode, const KernelParams&, cudaStream_t);
+    cudaError_t (*prepare)(int* data_ctas_per_sm);
+    cudaError_t (*launch)(int mode, const KernelParams&, cudaStream_t, int max_data_ctas, unsigned* grid_out, long long* items_out);
 };
 
 template <class PL>
@@ -56,28 +56,36 @@ template <class PL, int MINB>
 constexpr int pilot_minb() { return PL::P >= 32 ? (MINB < 2 ? MINB : 2) : MINB; }
 
 template <class PL, int MINB>
-cudaError_t prepare_impl()
+cudaError_t prepare_impl(int* data_ctas_per_sm)
 {
     cudaError_t e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_DATA, MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
+    e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_DATA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)PL::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    // resident data-kernel CTAs per SM: the persistent grid is this times the SM count
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS,
+                                                         PL::SMEM_BYTES);
 }
 
 template <class PL, int MINB>
-cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st)
+cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int max_data_ctas, unsigned* grid_out,
+                        long long* items_out)
 {
     if (mode == MODE_PILOT) {
         lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
-        unsigned grid;
+        long long items;
         if (PL::H_RING) {
-            grid = (unsigned)((long long)p.n_frames * ((p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS));
+            items = (long long)p.n_frames * ((p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS);
         } else {
             const long long n_work = (long long)p.n_frames * p.n_sym_work;
-            grid = (unsigned)((n_work + PL::TEAMS - 1) / PL::TEAMS);
+            items = (n_work + PL::TEAMS - 1) / PL::TEAMS;
         }
+        const unsigned grid = (unsigned)(items < max_data_ctas ? items : max_data_ctas);  // persistent CTAs
+        if (grid_out) *grid_out = grid;
+        if (items_out) *items_out = items;
         lsmrc_kernel<PL, MODE_DATA, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     }
     return cudaGetLastError();
@@ -151,6 +159,8 @@ struct ChanState {
     float* hsqrd = nullptr;           // [frames][K]
     float* epart = nullptr;           // [frames + kPilotCtaTarget][N]
     unsigned int* counters = nullptr; // [frames], zero between launches
+    unsigned long long* ticket = nullptr;  // data-kernel work-item counter, monotonic
+    unsigned long long ticket_next = 0;    // host mirror: value of *ticket once all enqueued launches have run
     int frames = 0;
 };
 constexpr int kPilotCtaTarget = 296;  // pilot kernel: aim for >= 2 CTAs per SM when frames are few
@@ -182,6 +192,7 @@ struct lsmrc_ctx {
     size_t slot_elems = 0;   // A*(N+C)
     size_t frame_elems = 0;  // S*slot
     const PlanOps* ops = nullptr;
+    int max_data_ctas = 1;  // persistent data-kernel grid: resident CTAs per SM x SM count
     float2* d_tw = nullptr;
     float2* d_pilot_bin = nullptr;
     bool have_pilot = false;
@@ -258,6 +269,7 @@ int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
     cudaFree(c.hsqrd);
     cudaFree(c.epart);
     cudaFree(c.counters);
+    cudaFree(c.ticket);
     c = ChanState();
     const size_t N = (size_t)h->cfg.fft_size;
     CK(h, cudaMalloc(&c.hwork, (size_t)frames * h->cfg.n_ant * N * sizeof(float2)));
@@ -265,12 +277,16 @@ int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
     CK(h, cudaMalloc(&c.epart, ((size_t)frames + kPilotCtaTarget) * N * sizeof(float)));
     CK(h, cudaMalloc(&c.counters, (size_t)frames * sizeof(unsigned int)));
     CK(h, cudaMemset(c.counters, 0, (size_t)frames * sizeof(unsigned int)));
+    CK(h, cudaMalloc(&c.ticket, sizeof(unsigned long long)));
+    CK(h, cudaMemset(c.ticket, 0, sizeof(unsigned long long)));
+    c.ticket_next = 0;
     c.frames = frames;
     return LSMRC_OK;
 }
 
 void free_chan(ChanState& c)
 {
+    cudaFree(c.ticket);
     cudaFree(c.hwork);
     cudaFree(c.hsqrd);
     cudaFree(c.epart);
@@ -298,7 +314,7 @@ int launch_pilot(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, f
     p.n_groups = pilot_groups(h, p.n_frames);
     p.epart = ch.epart;
     p.counters = ch.counters;
-    CK(h, h->ops->launch(MODE_PILOT, p, st));
+    CK(h, h->ops->launch(MODE_PILOT, p, st, h->max_data_ctas, nullptr, nullptr));
     h->launches++;
     return LSMRC_OK;
 }
@@ -310,7 +326,13 @@ int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, fl
     p.hwork = ch.hwork;
     p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
     p.n_groups = 1;
-    CK(h, h->ops->launch(MODE_DATA, p, st));
+    p.ticket = ch.ticket;
+    p.ticket_base = ch.ticket_next;
+    unsigned grid = 0;
+    long long items = 0;
+    CK(h, h->ops->launch(MODE_DATA, p, st, h->max_data_ctas, &grid, &items));
+    // every CTA draws tickets until it sees one past the end: items + grid draws in total
+    ch.ticket_next += (unsigned long long)items + grid;
     h->launches++;
     return LSMRC_OK;
 }
@@ -545,7 +567,12 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
         lsmrc_destroy(h);
         return fail(nullptr, rc, msg);
     };
-    if ((e = ops->prepare()) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute"); return bail(LSMRC_ERR_CUDA); }
+    {
+        int per_sm = 0;
+        if ((e = ops->prepare(&per_sm)) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute"); return bail(LSMRC_ERR_CUDA); }
+        if (per_sm < 1) { h->err = "data kernel does not fit on an SM"; return bail(LSMRC_ERR_CUDA); }
+        h->max_data_ctas = per_sm * prop.multiProcessorCount;
+    }
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(h, e, "cudaStreamCreate"); return bail(LSMRC_ERR_CUDA); }
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev2)) != cudaSuccess) { fail_cuda(h, e, "cudaEventCreate"); return bail(LSMRC_ERR_CUDA); }

@@ -72,6 +72,10 @@ struct KernelParams {
     int n_groups;
     float* epart;
     unsigned int* counters;
+    // data kernel only: work-item ticket counter (monotonic across launches on one stream) and its
+    // value when this launch starts; a CTA's next item is atomicAdd(ticket) - ticket_base
+    unsigned long long* ticket;
+    unsigned long long ticket_base;
     const float2* pilot_bin;  // X in FFT-bin order, K entries (bin k+1 at index k)
     // outputs of MODE_DATA
     float2* combined;  // [F][n_sym_work][K], ascending frequency
@@ -430,33 +434,17 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             }
         }
     } else {
-        // one team per (frame, data symbol); loop over all antennas, accumulate in registers
-        int f, s;
-        bool valid;
-        if constexpr (PL::H_RING) {
-            const int groups = (p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS;
-            f = blockIdx.x / groups;
-            s = (blockIdx.x % groups) * PL::TEAMS + team;
-            valid = s < p.n_sym_work;
-            if (!valid) s = p.n_sym_work - 1;
-        } else {
-            const long long n_work = (long long)p.n_frames * p.n_sym_work;
-            long long work = (long long)blockIdx.x * PL::TEAMS + team;
-            valid = work < n_work;
-            if (!valid) work = n_work - 1;
-            f = (int)(work / p.n_sym_work);
-            s = (int)(work % p.n_sym_work);
-        }
-        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)(p.first_sym + s) * p.sym_stride + p.cp;
-        const float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
-        float2 acc[P];
-#pragma unroll
-        for (int sl = 0; sl < P; ++sl) acc[sl] = make_float2(0.f, 0.f);
-
-        // Hconj ring: stage r%H_STAGES holds row r; full[] completes on the copy's bytes, empty[]
-        // when every team has consumed the row.  Thread 0 keeps H_AHEAD rows in flight ahead of
-        // the row being consumed; a stage is only refilled two rows after its last use, so the
-        // producer practically never waits on a straggling team.
+        // Persistent CTAs: the grid is sized to the SM count and every CTA pulls work items from a
+        // global ticket counter (dynamic, so faster SMs take more), so the twiddle table, the ring
+        // barriers and the launch ramp are paid once per CTA instead of once per item.  Work item = TEAMS (frame, data symbol) pairs -- of one
+        // frame when the Hconj ring is on -- one pair per team; each team loops over all antennas
+        // and accumulates in registers.
+        //
+        // Hconj ring: stage R%H_STAGES holds the R-th row this CTA consumes (R counts across
+        // items); full[] completes on the copy's bytes, empty[] when every team has consumed the
+        // row.  Thread 0 keeps H_AHEAD rows in flight ahead of the row being consumed; a stage is
+        // only refilled two rows after its last use, so the producer practically never waits on a
+        // straggling team.
         __shared__ __align__(8) uint64_t bar_full[PL::H_STAGES], bar_empty[PL::H_STAGES];
         constexpr uint32_t ROW_BYTES = N * sizeof(float2);
         if constexpr (PL::H_RING) {
@@ -468,11 +456,54 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                 mbar_fence_init();
             }
             __syncthreads();
+        }
+        const int groups = (p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS;
+        const long long n_work = (long long)p.n_frames * p.n_sym_work;
+        const int n_items = PL::H_RING ? p.n_frames * groups : (int)((n_work + PL::TEAMS - 1) / PL::TEAMS);
+        int rows_done = 0;  // ring rows consumed by this CTA so far
+
+        // producer side of the ring: refill the stage of ring row R with Hconj row `row` of `src`
+        auto ring_issue = [&](int R, const float2* src_row) {
+            const int sr = R % PL::H_STAGES;
+            const int use = R / PL::H_STAGES;
+            if (use > 0) mbar_wait(&bar_empty[sr], (uint32_t)((use - 1) & 1));
+            mbar_expect_tx(&bar_full[sr], ROW_BYTES);
+            bulk_g2s(s_hring + sr * N, src_row, ROW_BYTES, &bar_full[sr]);
+        };
+
+        __shared__ int s_item;
+        for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned long long tk = atomicAdd(p.ticket, 1ULL) - p.ticket_base;
+            s_item = tk < (unsigned long long)n_items ? (int)tk : -1;
+        }
+        __syncthreads();
+        const int item = s_item;
+        __syncthreads();  // s_item is rewritten by thread 0 at the top of the next round
+        if (item < 0) break;
+        int f, s;
+        bool valid;
+        if constexpr (PL::H_RING) {
+            f = item / groups;
+            s = (item % groups) * PL::TEAMS + team;
+            valid = s < p.n_sym_work;
+            if (!valid) s = p.n_sym_work - 1;
+        } else {
+            long long work = (long long)item * PL::TEAMS + team;
+            valid = work < n_work;
+            if (!valid) work = n_work - 1;
+            f = (int)(work / p.n_sym_work);
+            s = (int)(work % p.n_sym_work);
+        }
+        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)(p.first_sym + s) * p.sym_stride + p.cp;
+        const float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+        float2 acc[P];
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) acc[sl] = make_float2(0.f, 0.f);
+
+        if constexpr (PL::H_RING) {
             if (threadIdx.x == 0) {
-                for (int r = 0; r < PL::H_AHEAD && r < p.n_ant; ++r) {
-                    mbar_expect_tx(&bar_full[r], ROW_BYTES);
-                    bulk_g2s(s_hring + r * N, hw_frame + (long long)r * N, ROW_BYTES, &bar_full[r]);
-                }
+                for (int r = 0; r < PL::H_AHEAD && r < p.n_ant; ++r) ring_issue(rows_done + r, hw_frame + (long long)r * N);
             }
         }
 
@@ -487,12 +518,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             const float2* hw_row = hw_frame + (long long)a * N;
             if constexpr (PL::H_RING) {
                 const int r = a + PL::H_AHEAD;
-                if (threadIdx.x == 0 && r < p.n_ant) {
-                    const int sr = r % PL::H_STAGES, use = r / PL::H_STAGES;
-                    if (use > 0) mbar_wait(&bar_empty[sr], (uint32_t)((use - 1) & 1));
-                    mbar_expect_tx(&bar_full[sr], ROW_BYTES);
-                    bulk_g2s(s_hring + sr * N, hw_frame + (long long)r * N, ROW_BYTES, &bar_full[sr]);
-                }
+                if (threadIdx.x == 0 && r < p.n_ant) ring_issue(rows_done + r, hw_frame + (long long)r * N);
                 __syncwarp();
             }
             const float2* x_next = nullptr;
@@ -510,7 +536,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             if (PF_X > 0 && a + PF_X < p.n_ant)
                 prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X) * p.ant_stride, N, t);
             if (!PL::H_RING && PF_H > 0 && a + PF_H < p.n_ant) prefetch_row<T, true>(hw_row + (long long)PF_H * N, N, t);
-            const int st = a % PL::H_STAGES;
+            const int R = rows_done + a;
+            const int st = R % PL::H_STAGES;
             const float2* h_src = PL::H_RING ? (s_hring + st * N) : hw_row;
             bool h_ready = !PL::H_RING;
             row_fft<PL>(v, PL::REG_PF == 1 ? x_next : nullptr, tile, s_tw1, s_tw2, t, team,
@@ -518,7 +545,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                             // cpuLS.hpp:187-208: acc += Y * Hconj
                             if constexpr (PL::H_RING) {
                                 if (!h_ready) {
-                                    mbar_wait(&bar_full[st], (uint32_t)((a / PL::H_STAGES) & 1));
+                                    mbar_wait(&bar_full[st], (uint32_t)((R / PL::H_STAGES) & 1));
                                     h_ready = true;
                                 }
                                 acc[sl] = cmac(acc[sl], h_src[bin], y);
@@ -542,35 +569,44 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                             }
                         });
             if constexpr (PL::H_RING) {
-                __syncwarp();
+                team_sync<PL>(team);
                 if (t == 0) mbar_arrive(&bar_empty[st]);
             }
         }
+        rows_done += p.n_ant;
 
-        // epilogue: normalise (cpuLS.hpp:364-367), reorder (cpuLS.hpp:135-149), demap, pack
+        // epilogue: normalise (cpuLS.hpp:364-367), reorder (cpuLS.hpp:135-149), demap, pack.
+        // Specialised on the QAM order so the demapper and the bit packing are straight-line code.
         const float* e_row = p.hsqrd + (long long)f * K;
         float2* out_row = p.combined + ((long long)f * p.n_sym_work + s) * K;
         uint8_t* s_idx = reinterpret_cast<uint8_t*>(my_tiles);
-        team_sync<PL>(team);  // everyone is done reading the last tile before it is reused
+        uint8_t* bits_row = p.bits ? p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes : nullptr;
+        auto finish = [&](auto bconst) {
+            constexpr int b = decltype(bconst)::value;
+            float einv[P];
 #pragma unroll
-        for (int sl = 0; sl < P; ++sl) {
-            const int i = sl / PL::RL, j = sl % PL::RL;
-            const int bin = t + T * i + (N / PL::RL) * j;
-            if (bin > 0) {
-                const float e = e_row[bin - 1];
-                // 2-ulp reciprocal-multiply; well inside the 1e-5 parity tolerance
-                const float2 o = make_float2(__fdividef(acc[sl].x, e), __fdividef(acc[sl].y, e));
-                const int pos = (bin < N / 2) ? (bin - 1 + N / 2) : (bin - N / 2);
-                if (valid) out_row[pos] = o;
-                s_idx[pos] = (uint8_t)demap_symbol(o.x, o.y, p.qam_bits);
+            for (int sl = 0; sl < P; ++sl) {
+                const int i = sl / PL::RL, j = sl % PL::RL;
+                const int bin = t + T * i + (N / PL::RL) * j;
+                einv[sl] = __ldg(e_row + (bin > 0 ? bin - 1 : 0));
             }
-        }
-        if (p.bits != nullptr) {
-            team_sync<PL>(team);
-            uint8_t* bits_row = p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes;
-            // one output byte per thread and step; the symbol/bit split uses a compile-time b
-            auto pack = [&](auto bconst) {
-                constexpr int b = decltype(bconst)::value;
+            team_sync<PL>(team);  // everyone is done reading the last tile before it is reused
+#pragma unroll
+            for (int sl = 0; sl < P; ++sl) {
+                const int i = sl / PL::RL, j = sl % PL::RL;
+                const int bin = t + T * i + (N / PL::RL) * j;
+                if (bin > 0) {
+                    // one reciprocal, two multiplies (<= 2 ulp from the reference's two divisions,
+                    // far inside the 1e-5 parity tolerance)
+                    const float inv = __frcp_rn(einv[sl]);
+                    const float2 o = make_float2(acc[sl].x * inv, acc[sl].y * inv);
+                    const int pos = (bin < N / 2) ? (bin - 1 + N / 2) : (bin - N / 2);
+                    if (valid) out_row[pos] = o;
+                    s_idx[pos] = (uint8_t)demap_symbol(o.x, o.y, b);
+                }
+            }
+            if (bits_row != nullptr) {
+                team_sync<PL>(team);
                 for (int byte = t; byte < p.bits_row_bytes; byte += T) {
                     unsigned v8 = 0;
 #pragma unroll
@@ -581,11 +617,13 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                     }
                     if (valid) bits_row[byte] = (uint8_t)v8;
                 }
-            };
-            if (p.qam_bits == 2) pack(std::integral_constant<int, 2>{});
-            else if (p.qam_bits == 4) pack(std::integral_constant<int, 4>{});
-            else pack(std::integral_constant<int, 6>{});
-        }
+            }
+        };
+        if (p.qam_bits == 2) finish(std::integral_constant<int, 2>{});
+        else if (p.qam_bits == 4) finish(std::integral_constant<int, 4>{});
+        else finish(std::integral_constant<int, 6>{});
+        team_sync<PL>(team);  // the byte buffer aliases the tile the next item writes
+        }  // work items
     }
 }
 
