@@ -50,10 +50,13 @@ void fill_twiddles_impl(float2* tw)
             }
 }
 
+#ifndef LSMRC_PILOT_WIDE
+#define LSMRC_PILOT_WIDE 1
+#endif
 // the pilot kernel keeps the pilot, 1/|X|^2 and the energy partials of its P bins in registers on
 // top of the FFT working set: give the 32-point plans a 255-register budget there
 template <class PL, int MINB>
-constexpr int pilot_minb() { return PL::P >= 32 ? (MINB < 2 ? MINB : 2) : MINB; }
+constexpr int pilot_minb() { return (LSMRC_PILOT_WIDE && PL::P >= 32 && MINB > 2) ? 2 : MINB; }
 
 template <class PL, int MINB>
 cudaError_t prepare_impl(int* data_ctas_per_sm)
@@ -136,6 +139,44 @@ PlanOps make_ops()
 #define LSMRC_1024_HRING true
 #endif
 
+// knobs of the 2048- and 4096-point plans
+#ifndef LSMRC_2048_TEAMS
+#define LSMRC_2048_TEAMS 2
+#endif
+#ifndef LSMRC_2048_NBUF
+#define LSMRC_2048_NBUF 1
+#endif
+#ifndef LSMRC_2048_PFX
+#define LSMRC_2048_PFX 0
+#endif
+#ifndef LSMRC_2048_PFH
+#define LSMRC_2048_PFH 0
+#endif
+#ifndef LSMRC_2048_HRING
+#define LSMRC_2048_HRING false
+#endif
+#ifndef LSMRC_2048_MINB
+#define LSMRC_2048_MINB 3
+#endif
+#ifndef LSMRC_4096_TEAMS
+#define LSMRC_4096_TEAMS 1
+#endif
+#ifndef LSMRC_4096_NBUF
+#define LSMRC_4096_NBUF 1
+#endif
+#ifndef LSMRC_4096_PFX
+#define LSMRC_4096_PFX 0
+#endif
+#ifndef LSMRC_4096_PFH
+#define LSMRC_4096_PFH 0
+#endif
+#ifndef LSMRC_4096_HRING
+#define LSMRC_4096_HRING false
+#endif
+#ifndef LSMRC_4096_MINB
+#define LSMRC_4096_MINB 3
+#endif
+
 // One plan per FFT size (64..4096).  N/P threads own a row; see lsmrc_kernels.cuh.
 const PlanOps* find_plan(int N)
 {
@@ -145,8 +186,8 @@ const PlanOps* find_plan(int N)
         make_ops<Plan<256, 16, 16, 1, 8>, 4>(),
         make_ops<Plan<512, 32, 16, 1, 8>, 3>(),
         make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>, LSMRC_1024_MINB>(),
-        make_ops<Plan<2048, 32, 16, 4, 2>, 3>(),
-        make_ops<Plan<4096, 32, 32, 4, 1>, 3>(),
+        make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>, LSMRC_2048_MINB>(),
+        make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>, LSMRC_4096_MINB>(),
     };
     for (const PlanOps& o : plans)
         if (o.N == N) return &o;

@@ -37,6 +37,9 @@
 
 #include "fft_radix.cuh"
 
+#ifndef LSMRC_TW_REGS
+#define LSMRC_TW_REGS 0
+#endif
 #ifndef LSMRC_H_STAGES
 #define LSMRC_H_STAGES 3
 #endif
@@ -99,6 +102,7 @@ struct Plan {
     static constexpr bool H_RING = H_RING_;
     static constexpr int H_STAGES = LSMRC_H_STAGES;   // ring depth
     static constexpr int H_AHEAD = LSMRC_H_STAGES - 2; // rows kept in flight ahead of the row being consumed
+    static constexpr bool TW_REGS = LSMRC_TW_REGS != 0 && H_RING_;  // stage-1 twiddles in registers (data kernel)
     static constexpr int TW_CHUNK = (P_ >= 8) ? LSMRC_TW_CHUNK : P_;  // inter-stage twiddles fetched this many at a time
     static constexpr int HRING = H_RING_ ? H_STAGES * N_ : 0;  // complex elements
     // PF_X: rows ahead whose antenna-samples are prefetched into L2; PF_H: rows ahead whose
@@ -260,10 +264,20 @@ __device__ __forceinline__ void row_load(float2 (&v)[PL::P], const float2* __res
 template <class PL, class Sink>
 __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __restrict__ x_next,
                                         float2* __restrict__ tile, const float2* __restrict__ s_tw1,
-                                        const float2* __restrict__ s_tw2, int t, int team, Sink&& sink)
+                                        const float2* __restrict__ s_tw2, int t, int team, Sink&& sink,
+                                        const float2* tw_regs = nullptr)
 {
     constexpr int P = PL::P, T = PL::T, ROW = PL::ROW, R2 = PL::R2, R3 = PL::R3;
     fft_reg<P>(v);
+    if (PL::TW_REGS && tw_regs != nullptr) {
+        // inter-stage twiddles held in registers for the whole kernel (they depend on the lane only)
+#pragma unroll
+        for (int k1 = 0; k1 < P; ++k1) {
+            float2 val = v[brev<P>(k1)];
+            if (k1 > 0) val = cmul(val, tw_regs[k1 - 1]);
+            tile[k1 * ROW + t] = val;
+        }
+    } else {
     // Inter-stage twiddles W_N^(t*k1) come from the shared table.  They are fetched in chunks of
     // TWC, one chunk ahead of the multiplies that use them, through volatile loads fenced with
     // compiler barriers: left to itself ptxas (168-register budget) sinks every twiddle load to
@@ -291,6 +305,7 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
         asm volatile("" ::: "memory");
 #pragma unroll
         for (int j = 0; j < TWC; ++j) twa[j] = twb[j];
+    }
     }
     if (x_next != nullptr) row_load<PL>(v, x_next, t);
     team_sync<PL>(team);
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
             row_fft<PL>(v, nullptr, tile, s_tw1, s_tw2, t, team,
                         [&](int sl, int bin, float2 z) {
-                            // LS estimate, naive complex division of cpuLS.hpp:233-244, then conj (:303-307)
+                            // LS estimate, complex division of cpuLS.hpp:233-244, then conj (:303-307)
                             const float2 X = xp[sl];
                             const float re = (z.x * X.x + z.y * X.y) * xden[sl];
                             const float im = (z.y * X.x - z.x * X.y) * xden[sl];
@@ -471,6 +486,11 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             bulk_g2s(s_hring + sr * N, src_row, ROW_BYTES, &bar_full[sr]);
         };
 
+        float2 twr[PL::TW_REGS ? P - 1 : 1];
+        if constexpr (PL::TW_REGS) {
+#pragma unroll
+            for (int k1 = 1; k1 < P; ++k1) twr[k1 - 1] = s_tw1[(k1 - 1) * T + t];
+        }
         __shared__ int s_item;
         for (;;) {
         if (threadIdx.x == 0) {
@@ -567,7 +587,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 #endif
                                 acc[sl] = cmac(acc[sl], h, y);
                             }
-                        });
+                        },
+                        PL::TW_REGS ? twr : nullptr);
             if constexpr (PL::H_RING) {
                 team_sync<PL>(team);
                 if (t == 0) mbar_arrive(&bar_empty[st]);
