@@ -39,6 +39,14 @@ ABI = {
     "lsmrc_ring_submit_split": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "lsmrc_ring_wait": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "lsmrc_ring_copy_done": (c_int, [c_void_p, c_int]),
+    "lsmrc_stage_drop_prefix": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong]),
+    "lsmrc_stage_fft": (c_int, [c_void_p, c_void_p, c_longlong]),
+    "lsmrc_stage_find_hs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsmrc_stage_find_hsqrd": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lsmrc_stage_mult_conj": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "lsmrc_stage_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "lsmrc_stage_shift_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong]),
+    "lsmrc_copy_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "lsmrc_dev_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "lsmrc_dev_free": (c_int, [c_void_p, c_void_p]),
     "lsmrc_copy_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
@@ -209,6 +217,11 @@ class LsMrcReceiver:
         comb = np.ctypeslib.as_array(ctypes.cast(c, POINTER(c_float)), shape=(nd, self.K, 2)).view(np.complex64)[..., 0]
         bits = np.ctypeslib.as_array(ctypes.cast(b, POINTER(ctypes.c_uint8)), shape=(nd, self.row_bytes))
         return comb, bits
+
+    # -- stand-alone steps (device pointers / torch tensors)
+    def stage(self, name, *args):
+        fn = getattr(self.lib, "lsmrc_stage_" + name)
+        self._ck(fn(self.h, *[_ptr(a) for a in args]))
 
     # -- plumbing
     def host_alloc(self, nbytes):

@@ -67,6 +67,9 @@ cudaError_t prepare_impl(int* data_ctas_per_sm)
     e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_DATA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)PL::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_FFT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)PL::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     // resident data-kernel CTAs per SM: the persistent grid is this times the SM count
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS,
                                                          PL::SMEM_BYTES);
@@ -76,7 +79,11 @@ template <class PL, int MINB>
 cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int max_data_ctas, unsigned* grid_out,
                         long long* items_out)
 {
-    if (mode == MODE_PILOT) {
+    if (mode == MODE_FFT) {
+        const long long groups = ((long long)p.n_frames + PL::TEAMS - 1) / PL::TEAMS;
+        const unsigned grid = (unsigned)(groups < 4 * (long long)max_data_ctas ? groups : 4 * (long long)max_data_ctas);
+        lsmrc_kernel<PL, MODE_FFT, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+    } else if (mode == MODE_PILOT) {
         lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
         long long items;
@@ -902,6 +909,111 @@ int lsmrc_ring_wait(lsmrc_handle h, int lane, const void** combined, const void*
     if (combined) *combined = L.h_comb;
     if (bits) *bits = L.h_bits;
     if (hconj) *hconj = L.h_hconj;
+    return LSMRC_OK;
+}
+
+// ---- stand-alone steps (the kernel-wrapper methods of gpuLS.cuh:87-99) -------------------------------
+
+static unsigned ew_grid(long long n) { long long g = (n + 255) / 256; return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g)); }
+
+int lsmrc_stage_drop_prefix(lsmrc_handle h, void* d_out, const void* d_in, long long rows)
+{
+    if (!h || !d_out || !d_in || rows < 0) return fail(h, LSMRC_ERR_INVALID, "bad argument");
+    if (rows == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_drop_prefix<<<ew_grid(rows * h->cfg.fft_size), 256, 0, compute_stream(h)>>>(
+        static_cast<float2*>(d_out), static_cast<const float2*>(d_in), rows, h->cfg.fft_size, h->cfg.cp_len);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_stage_fft(lsmrc_handle h, void* d_rows, long long rows)
+{
+    if (!h || !d_rows || rows < 0 || rows > 0x7fffffffLL) return fail(h, LSMRC_ERR_INVALID, "bad argument");
+    if (rows == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    KernelParams p = base_params(h);
+    p.rx = static_cast<const float2*>(d_rows);
+    p.combined = static_cast<float2*>(d_rows);
+    p.ant_stride = h->cfg.fft_size;
+    p.cp = 0;
+    p.n_frames = (int)rows;
+    CK(h, h->ops->launch(MODE_FFT, p, compute_stream(h), h->max_data_ctas, nullptr, nullptr));
+    h->launches++;
+    return LSMRC_OK;
+}
+
+int lsmrc_stage_find_hs(lsmrc_handle h, const void* d_yfft, void* d_hconj, const void* d_x)
+{
+    if (!h || !d_yfft || !d_hconj) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (!d_x && !h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first or pass dX");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int A = h->cfg.n_ant, N = h->cfg.fft_size;
+    k_find_hs<<<ew_grid((long long)A * h->K), 256, 0, compute_stream(h)>>>(
+        static_cast<const float2*>(d_yfft), static_cast<float2*>(d_hconj),
+        d_x ? static_cast<const float2*>(d_x) : h->d_pilot_bin, A, N, d_x ? h->K : 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_stage_find_hsqrd(lsmrc_handle h, const void* d_hconj, void* d_hsqrd)
+{
+    if (!h || !d_hconj || !d_hsqrd) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_find_hsqrd<<<ew_grid(h->K), 256, 0, compute_stream(h)>>>(static_cast<const float2*>(d_hconj),
+                                                               static_cast<float*>(d_hsqrd), h->cfg.n_ant, h->K);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_stage_mult_conj(lsmrc_handle h, const void* d_yfft, const void* d_hconj, void* d_yf, int n_syms)
+{
+    if (!h || !d_yfft || !d_hconj || !d_yf || n_syms < 0) return fail(h, LSMRC_ERR_INVALID, "bad argument");
+    if (n_syms == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_mult_conj<<<ew_grid((long long)n_syms * h->cfg.n_ant * h->K), 256, 0, compute_stream(h)>>>(
+        static_cast<const float2*>(d_yfft), static_cast<const float2*>(d_hconj), static_cast<float2*>(d_yf), n_syms,
+        h->cfg.n_ant, h->cfg.fft_size);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_stage_combine(lsmrc_handle h, const void* d_yf, const void* d_hsqrd, void* d_out, int n_syms)
+{
+    if (!h || !d_yf || !d_hsqrd || !d_out || n_syms < 0) return fail(h, LSMRC_ERR_INVALID, "bad argument");
+    if (d_out == d_yf) return fail(h, LSMRC_ERR_INVALID, "d_out must not alias d_yf (the reference's in-place form races, gpuLS.cu:244-256)");
+    if (n_syms == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_combine<<<ew_grid((long long)n_syms * h->K), 256, 0, compute_stream(h)>>>(
+        static_cast<const float2*>(d_yf), static_cast<const float*>(d_hsqrd), static_cast<float2*>(d_out), n_syms,
+        h->cfg.n_ant, h->K);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_stage_shift_rows(lsmrc_handle h, const void* d_in, void* d_out, long long rows)
+{
+    if (!h || !d_in || !d_out || rows < 0) return fail(h, LSMRC_ERR_INVALID, "bad argument");
+    if (d_in == d_out) return fail(h, LSMRC_ERR_INVALID, "d_out must not alias d_in");
+    if (rows == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_shift_rows<<<ew_grid(rows * h->K), 256, 0, compute_stream(h)>>>(static_cast<const float2*>(d_in),
+                                                                       static_cast<float2*>(d_out), rows, h->K);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_copy_device(lsmrc_handle h, void* d_dst, const void* d_src, size_t bytes)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, compute_stream(h)));
     return LSMRC_OK;
 }
 

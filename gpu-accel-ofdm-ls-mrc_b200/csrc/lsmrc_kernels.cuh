@@ -49,7 +49,7 @@
 
 namespace lsmrc {
 
-enum { MODE_PILOT = 0, MODE_DATA = 1 };
+enum { MODE_PILOT = 0, MODE_DATA = 1, MODE_FFT = 2 };
 
 struct KernelParams {
     // input: antenna-samples, complex64.  element (f, s, a, n) at
@@ -366,7 +366,25 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
     const int t = threadIdx.x % T;
     float2* my_tiles = s_tiles + team * (PL::NBUF * PL::TILE);
 
-    if constexpr (MODE == MODE_PILOT) {
+    if constexpr (MODE == MODE_FFT) {
+        // stand-alone batched transform (gpuLS::batchedFFT, gpuLS.cu:343-349): p.rx holds
+        // p.n_frames rows of N samples (row stride p.ant_stride), transformed in place into
+        // p.combined (may alias p.rx: a team has its whole row in registers before it stores)
+        const int n_rows = p.n_frames;
+        for (int row0 = blockIdx.x * PL::TEAMS; row0 < n_rows; row0 += gridDim.x * PL::TEAMS) {
+            const int row_raw = row0 + team;
+            const bool ok = row_raw < n_rows;
+            const int row = ok ? row_raw : n_rows - 1;
+            float2 v[P];
+            row_load<PL>(v, p.rx + (long long)row * p.ant_stride + p.cp, t);
+            float2* out = p.combined + (long long)row * N;
+            team_sync<PL>(team);
+            row_fft<PL>(v, nullptr, my_tiles, s_tw1, s_tw2, t, team, [&](int, int bin, float2 y) {
+                if (ok) out[bin] = y;
+            });
+            team_sync<PL>(team);
+        }
+    } else if constexpr (MODE == MODE_PILOT) {
         // CTA (f, g): frame f, antenna group g of n_groups; inside the CTA the antennas of the
         // group are dealt round-robin to the teams
         const int f = blockIdx.x / p.n_groups;
@@ -645,6 +663,91 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         else finish(std::integral_constant<int, 6>{});
         team_sync<PL>(team);  // the byte buffer aliases the tile the next item writes
         }  // work items
+    }
+}
+
+// ---- stand-alone per-step kernels: the individually callable steps of gpuLS.cuh:87-99 -----------
+// (the fused kernels above never use them; they exist so that callers of the reference's
+// wrapper methods get the same intermediate tensors)
+
+// gpuLS.cu:143-156 dropPrefix: out[r][n] = in[r][n + cp]
+__global__ void k_drop_prefix(float2* __restrict__ out, const float2* __restrict__ in, long long rows, int n, int cp)
+{
+    const long long total = rows * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n;
+        const int c = (int)(i - r * n);
+        out[i] = in[r * (n + cp) + cp + c];
+    }
+}
+
+// gpuLS.cu:158-182 findHs: hconj[a][k] = conj(yfft[a][k+1] / x[k])   (x: K entries, bin order)
+__global__ void k_find_hs(const float2* __restrict__ yfft, float2* __restrict__ hconj, const float2* __restrict__ x,
+                          int rows, int n, int x_row_stride)
+{
+    const int K = n - 1;
+    const long long total = (long long)rows * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i / K), k = (int)(i - (long long)a * K);
+        const float2 z = yfft[(long long)a * n + k + 1];
+        const float2 X = x[(long long)a * x_row_stride + k];
+        const float den = X.x * X.x + X.y * X.y;
+        hconj[i] = make_float2((z.x * X.x + z.y * X.y) / den, -((z.y * X.x - z.x * X.y) / den));
+    }
+}
+
+// gpuLS.cu:185-209 findDistSqrd: hsqrd[k] = sum_a |h[a][k]|^2  (sequential over a: the CPU order)
+__global__ void k_find_hsqrd(const float2* __restrict__ h, float* __restrict__ hsqrd, int rows, int K)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int a = 0; a < rows; ++a) {
+            const float2 v = h[(long long)a * K + k];
+            acc += v.x * v.x + v.y * v.y;
+        }
+        hsqrd[k] = acc;
+    }
+}
+
+// gpuLS.cu:212-233 multiplyWithChannelConj: yf[s][a][k] = yfft[s][a][k+1] * hconj[a][k]
+__global__ void k_mult_conj(const float2* __restrict__ yfft, const float2* __restrict__ hconj, float2* __restrict__ yf,
+                            int syms, int rows, int n)
+{
+    const int K = n - 1;
+    const long long per_sym = (long long)rows * K, total = per_sym * syms;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long sy = i / per_sym, r = i - sy * per_sym;
+        const int a = (int)(r / K), k = (int)(r - (long long)a * K);
+        yf[i] = cmul(yfft[(sy * rows + a) * n + k + 1], hconj[r]);
+    }
+}
+
+// gpuLS.cu:236-259 combineForMRC: out[s][k] = (sum_a yf[s][a][k]) / hsqrd[k]   (out must not alias yf)
+__global__ void k_combine(const float2* __restrict__ yf, const float* __restrict__ hsqrd, float2* __restrict__ out, int syms,
+                          int rows, int K)
+{
+    const long long total = (long long)syms * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long sy = i / K;
+        const int k = (int)(i - sy * K);
+        float2 acc = make_float2(0.f, 0.f);
+        for (int a = 0; a < rows; ++a) acc = cadd(acc, yf[(sy * rows + a) * K + k]);
+        const float e = hsqrd[k];
+        out[i] = make_float2(acc.x / e, acc.y / e);
+    }
+}
+
+// gpuLS.cu:109-125 shiftOneRow: out[r][i] = in[r][(i + (K-1)/2) mod K]   (out must not alias in)
+__global__ void k_shift_rows(const float2* __restrict__ in, float2* __restrict__ out, long long rows, int K)
+{
+    const long long total = rows * K;
+    const int sh = (K - 1) / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        const int c = (int)(i - r * K);
+        int src = c + sh;
+        if (src >= K) src -= K;
+        out[i] = in[r * K + src];
     }
 }
 

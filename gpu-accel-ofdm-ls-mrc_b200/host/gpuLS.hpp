@@ -134,16 +134,62 @@ class gpuLS {
         for (int i = 0; i < cols; ++i) r[i] = t[(size_t)((i + (cols - 1) / 2) % cols)];
     }
 
-    // The six per-step kernel wrappers of gpuLS.cuh:87-99.  Their work (CP strip, FFT, LS divide,
-    // |H|^2 sum, multiply by conj(H), antenna combine, output roll) is fused into the two kernels
-    // behind firstVector / demod*; called on their own they are no-ops that say so once.
-    void ShiftOneRow(cuFloatComplex*, int, int, dim3, dim3, cudaStream_t*) { fused("ShiftOneRow"); }
-    void DropPrefix(cuFloatComplex*, cuFloatComplex*, int, int, dim3, dim3, cudaStream_t*) { fused("DropPrefix"); }
-    void FindLeastSquaresGPU(cuFloatComplex*, cuFloatComplex*, cuFloatComplex*, int, int, dim3, dim3, cudaStream_t*) { fused("FindLeastSquaresGPU"); }
-    void FindHsqrdforMRC(cuFloatComplex*, float*, int, int, dim3, dim3, cudaStream_t*) { fused("FindHsqrdforMRC"); }
-    void MultiplyWithChannelConj(cuFloatComplex*, cuFloatComplex*, cuFloatComplex*, int, int, int, dim3, dim3, cudaStream_t*) { fused("MultiplyWithChannelConj"); }
-    void CombineForMRC(cuFloatComplex*, float*, int, int, dim3, dim3, cudaStream_t*) { fused("CombineForMRC"); }
-    void batchedFFT(cuFloatComplex*, int, int, cudaStream_t*) { fused("batchedFFT"); }
+    // The per-step kernel wrappers of gpuLS.cuh:87-99, for callers that drive the chain step by step
+    // on their own device buffers.  (firstVector / demod* do NOT go through these: there the steps
+    // are fused into two kernels.)  The reference derives the amount of work from the launch
+    // geometry the caller passes; the same convention is honoured here: rows of work =
+    // grid.y * block.y where the reference indexes that way, and the stream argument is accepted
+    // but the work runs on the handle's stream.
+    // gpuLS.cu:263-266 / kernel :109-125 -- roll every length-`cols` row to ascending frequency, in place
+    void ShiftOneRow(cuFloatComplex* Y, int cols, int rows, dim3 block, dim3 grid, cudaStream_t*)
+    {
+        (void)rows;
+        needK(cols);
+        const long long n_rows = (long long)grid.y * block.y;
+        void* tmp = scratch((size_t)n_rows * cols * sizeof(cuFloatComplex));
+        check(lsmrc_stage_shift_rows(handle, Y, tmp, n_rows), "lsmrc_stage_shift_rows");
+        check(lsmrc_copy_device(handle, Y, tmp, (size_t)n_rows * cols * sizeof(cuFloatComplex)), "lsmrc_copy_device");
+    }
+    // gpuLS.cu:268-271 / :143-156 -- Y[r][n] = dY[r][n + prefix]
+    void DropPrefix(cuFloatComplex* Y, cuFloatComplex* dY, int rows, int cols, dim3, dim3, cudaStream_t*)
+    {
+        needN(cols);
+        check(lsmrc_stage_drop_prefix(handle, Y, dY, rows), "lsmrc_stage_drop_prefix");
+    }
+    // gpuLS.cu:273-276 / :158-182 -- dH[a][k] = conj(dY[a][k+1] / dX[a][k]); dY holds the FFT of the pilot symbol
+    void FindLeastSquaresGPU(cuFloatComplex* dY, cuFloatComplex* dH, cuFloatComplex* dX, int rows, int cols, dim3, dim3, cudaStream_t*)
+    {
+        checkDims(rows, cols);
+        check(lsmrc_stage_find_hs(handle, dY, dH, dX), "lsmrc_stage_find_hs");
+    }
+    // gpuLS.cu:278-282 / :185-209 -- Hsqrd[k] = sum_a |H[a][k]|^2   (cols here is K = N-1, as in the reference)
+    void FindHsqrdforMRC(cuFloatComplex* H, float* Hsqrd, int rows, int cols, dim3, dim3, cudaStream_t*)
+    {
+        checkDims(rows, cols + 1);
+        check(lsmrc_stage_find_hsqrd(handle, H, Hsqrd), "lsmrc_stage_find_hsqrd");
+    }
+    // gpuLS.cu:284-287 / :212-233 -- Yf[s][a][k] = Y[s][a][k+1] * Hconj[a][k] for `syms` symbols
+    void MultiplyWithChannelConj(cuFloatComplex* Y, cuFloatComplex* Hconj, cuFloatComplex* Yf, int rows, int cols, int syms, dim3, dim3, cudaStream_t*)
+    {
+        checkDims(rows, cols);
+        check(lsmrc_stage_mult_conj(handle, Y, Hconj, Yf, syms), "lsmrc_stage_mult_conj");
+    }
+    // gpuLS.cu:289-293 / :236-259 -- Y[s*K + k] = sum_a Y[s][a][k] / Hsqrd[k], symbols = grid.y, written back into
+    // the head of Y as the reference does (through a scratch buffer: the reference's in-place form races)
+    void CombineForMRC(cuFloatComplex* Y, float* Hsqrd, int rows, int cols, dim3, dim3 grid, cudaStream_t*)
+    {
+        checkDims(rows, cols + 1);
+        const int syms = (int)grid.y;
+        void* tmp = scratch((size_t)syms * cols * sizeof(cuFloatComplex));
+        check(lsmrc_stage_combine(handle, Y, Hsqrd, tmp, syms), "lsmrc_stage_combine");
+        check(lsmrc_copy_device(handle, Y, tmp, (size_t)syms * cols * sizeof(cuFloatComplex)), "lsmrc_copy_device");
+    }
+    // gpuLS.cu:343-349 -- in-place forward FFT of `rows` rows of `cols` points (hand-written kernel, no cuFFT plan)
+    void batchedFFT(cuFloatComplex* Y, int rows, int cols, cudaStream_t*)
+    {
+        needN(cols);
+        check(lsmrc_stage_fft(handle, Y, rows), "lsmrc_stage_fft");
+    }
 
     // Pilot symbol: next ring slot -> H.  gpuLS.cu:351-408.
     void firstVector(cuFloatComplex* dY, cuFloatComplex* Y, cuFloatComplex* dH, cuFloatComplex* dX, float* Hsqrd,
@@ -241,15 +287,35 @@ class gpuLS {
             exit(EXIT_FAILURE);
         }
     }
-    void fused(const char* name)
+    void needN(int cols)
     {
-        static bool said = false;
-        if (!said) fprintf(stderr, "gpuLS::%s: this step is fused into firstVector/demod*; the stand-alone call does nothing\n", name);
-        said = true;
+        if (cols != cols_) {
+            fprintf(stderr, "gpuLS: called with %d columns but the handle was created for FFT size %d\n", cols, cols_);
+            exit(EXIT_FAILURE);
+        }
+    }
+    void needK(int cols)
+    {
+        if (cols != cols_ - 1) {
+            fprintf(stderr, "gpuLS: called with rows of %d but the handle has %d used subcarriers\n", cols, cols_ - 1);
+            exit(EXIT_FAILURE);
+        }
+    }
+    void* scratch(size_t bytes)
+    {
+        if (bytes > scratch_bytes_) {
+            if (d_scratch_) lsmrc_dev_free(handle, d_scratch_);
+            d_scratch_ = nullptr;
+            check(lsmrc_dev_alloc(handle, bytes, &d_scratch_), "lsmrc_dev_alloc");
+            scratch_bytes_ = bytes;
+        }
+        return d_scratch_;
     }
     int rows_, cols_, cp_, n_sym_;
     std::vector<uint8_t> bits_;
     void* d_comb_ = nullptr;
+    void* d_scratch_ = nullptr;
+    size_t scratch_bytes_ = 0;
 };
 
 // ---- free-function spellings used by gpuLS_main.cu:104-141 ------------------------------------------

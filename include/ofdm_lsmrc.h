@@ -127,6 +127,28 @@ int lsmrc_ring_wait(lsmrc_handle h, int lane, const void **combined, const void 
                     const void **hconj);
 int lsmrc_ring_copy_done(lsmrc_handle h, int lane); /* blocks until the lane's H2D finished (slots reusable) */
 
+/* ---- stand-alone steps: the individually callable kernel wrappers of gpuLS.cuh:87-99.  The fused
+ *      entry points above never go through them; they produce the same intermediate tensors the
+ *      reference's wrappers do, for callers that drive the chain step by step.  DEVICE pointers,
+ *      enqueued on the compute stream.  A = n_ant, N = fft_size, K = N-1. ------------------------- */
+/* DropPrefix (gpuLS.cu:143-156,268-271): out[r][n] = in[r][n + cp], in [rows][N+C] -> out [rows][N] */
+int lsmrc_stage_drop_prefix(lsmrc_handle h, void *d_out, const void *d_in, long long rows);
+/* batchedFFT (gpuLS.cu:343-349): in-place forward N-point DFT of `rows` rows [rows][N] */
+int lsmrc_stage_fft(lsmrc_handle h, void *d_rows, long long rows);
+/* FindLeastSquaresGPU / findHs (gpuLS.cu:158-182,273-276): hconj[a][k] = conj(yfft[a][k+1] / X[a][k]);
+ * d_x is the reference's replicated pilot [A][K] in bin order, or NULL for the handle's pilot */
+int lsmrc_stage_find_hs(lsmrc_handle h, const void *d_yfft, void *d_hconj, const void *d_x);
+/* FindHsqrdforMRC / findDistSqrd (gpuLS.cu:185-209,278-282): hsqrd[k] = sum_a |hconj[a][k]|^2 */
+int lsmrc_stage_find_hsqrd(lsmrc_handle h, const void *d_hconj, void *d_hsqrd);
+/* MultiplyWithChannelConj (gpuLS.cu:212-233,284-287): yf[s][a][k] = yfft[s][a][k+1] * hconj[a][k] */
+int lsmrc_stage_mult_conj(lsmrc_handle h, const void *d_yfft, const void *d_hconj, void *d_yf, int n_syms);
+/* CombineForMRC (gpuLS.cu:236-259,289-293): out[s][k] = sum_a yf[s][a][k] / hsqrd[k]; out must not
+ * alias yf (the reference writes in place and races between blocks) */
+int lsmrc_stage_combine(lsmrc_handle h, const void *d_yf, const void *d_hsqrd, void *d_out, int n_syms);
+/* ShiftOneRow (gpuLS.cu:109-125,263-266): out[r][i] = in[r][(i + (K-1)/2) mod K], rows of K */
+int lsmrc_stage_shift_rows(lsmrc_handle h, const void *d_in, void *d_out, long long rows);
+int lsmrc_copy_device(lsmrc_handle h, void *d_dst, const void *d_src, size_t bytes); /* D2D on the compute stream */
+
 /* ---- memory and stream plumbing, so callers need no CUDA headers (replaces the raw
  *      cudaMalloc/cudaMemcpy/cudaFree calls of gpuLS_main.cu:73-91,135-139) ------------ */
 int lsmrc_dev_alloc(lsmrc_handle h, size_t bytes, void **d_ptr);

@@ -117,3 +117,41 @@ def test_full_size_round_trip_and_linearity(ofdm, name, frames):
         r.demod_frames_device(torch.view_as_real(rx2), frames, comb2, None)
         r.sync()
         assert torch.allclose(comb2, comb * g, rtol=1e-5, atol=1e-6)
+
+
+def test_standalone_steps_reproduce_the_chain(ofdm, oracle):
+    """The individually callable steps (gpuLS.cuh:87-99 wrappers -> lsmrc_stage_*) chained by hand give the
+    oracle's Hconj, sum|H|^2 and combined symbols; the batched FFT alone matches numpy."""
+    import torch
+
+    A, N, C, S, b = 8, 1024, 64, 4, 4
+    K = N - 1
+    d = ofdm.synth.make_frames(1, A, N, C, S, b, snr_db=15.0, seed=33)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    dev = torch.device("cuda:0")
+    rx = torch.view_as_real(torch.from_numpy(d["rx"][0]).to(dev)).contiguous()            # [S][A][N+C][2]
+    y = torch.empty((S, A, N, 2), device=dev)
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(d["pilot_asc"])
+        r.stage("drop_prefix", y, rx, S * A)
+        r.sync()
+        assert torch.equal(y, rx[:, :, C:, :])
+        r.stage("fft", y, S * A)
+        r.sync()
+        want = np.fft.fft(d["rx"][0][:, :, C:].astype(np.complex128), axis=-1)
+        got = torch.view_as_complex(y).cpu().numpy()
+        assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+        hconj = torch.empty((A, K, 2), device=dev)
+        hsq = torch.empty((K,), device=dev)
+        r.stage("find_hs", y[0], hconj, None)
+        r.stage("find_hsqrd", hconj, hsq)
+        yf = torch.empty((S - 1, A, K, 2), device=dev)
+        r.stage("mult_conj", y[1:].contiguous(), hconj, yf, S - 1)
+        comb = torch.empty((S - 1, K, 2), device=dev)
+        r.stage("combine", yf, hsq, comb, S - 1)
+        out = torch.empty_like(comb)
+        r.stage("shift_rows", comb, out, S - 1)
+        r.sync()
+    assert_close(torch.view_as_complex(hconj).cpu().numpy(), ref["hconj"][0], "stage Hconj")
+    assert_close(hsq.cpu().numpy(), ref["hsqrd"][0], "stage sum|H|^2")
+    assert_close(torch.view_as_complex(out).cpu().numpy(), ref["combined"][0], "stage combined")
