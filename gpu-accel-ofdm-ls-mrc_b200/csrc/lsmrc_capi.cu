@@ -87,16 +87,26 @@ cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int ma
         lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
         long long items;
+        KernelParams q = p;
         if (PL::H_RING) {
             items = (long long)p.n_frames * ((p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS);
+            q.ant_split = 1;
         } else {
+            // few (frame, symbol) pairs: split each pair's antennas over several teams of a CTA so that
+            // more of the GPU works on the batch (single-frame latency); many pairs: one team per pair
             const long long n_work = (long long)p.n_frames * p.n_sym_work;
-            items = (n_work + PL::TEAMS - 1) / PL::TEAMS;
+            int as = 1;
+            while (as * 2 <= PL::TEAMS && as * 2 <= p.n_ant &&
+                   (n_work * (as * 2) + PL::TEAMS - 1) / PL::TEAMS <= (long long)max_data_ctas / 2)
+                as *= 2;
+            q.ant_split = as;
+            const int slots = PL::TEAMS / as;
+            items = (n_work + slots - 1) / slots;
         }
         const unsigned grid = (unsigned)(items < max_data_ctas ? items : max_data_ctas);  // persistent CTAs
         if (grid_out) *grid_out = grid;
         if (items_out) *items_out = items;
-        lsmrc_kernel<PL, MODE_DATA, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+        lsmrc_kernel<PL, MODE_DATA, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(q);
     }
     return cudaGetLastError();
 }
@@ -146,6 +156,17 @@ PlanOps make_ops()
 #define LSMRC_1024_HRING true
 #endif
 
+// knobs of the small plans (64..512 points): rows of x prefetched to L2, rows of Hconj prefetched to L1,
+// register double-buffering of the next row
+#ifndef LSMRC_SMALL_PFX
+#define LSMRC_SMALL_PFX 0
+#endif
+#ifndef LSMRC_SMALL_PFH
+#define LSMRC_SMALL_PFH 0
+#endif
+#ifndef LSMRC_SMALL_REGPF
+#define LSMRC_SMALL_REGPF 0
+#endif
 // knobs of the 2048- and 4096-point plans
 #ifndef LSMRC_2048_TEAMS
 #define LSMRC_2048_TEAMS 2
@@ -188,10 +209,10 @@ PlanOps make_ops()
 const PlanOps* find_plan(int N)
 {
     static const PlanOps plans[] = {
-        make_ops<Plan<64, 16, 4, 1, 32>, 4>(),
-        make_ops<Plan<128, 16, 8, 1, 16>, 4>(),
-        make_ops<Plan<256, 16, 16, 1, 8>, 4>(),
-        make_ops<Plan<512, 32, 16, 1, 8>, 3>(),
+        make_ops<Plan<64, 16, 4, 1, 32, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, 4>(),
+        make_ops<Plan<128, 16, 8, 1, 16, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, 4>(),
+        make_ops<Plan<256, 16, 16, 1, 8, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, 4>(),
+        make_ops<Plan<512, 32, 16, 1, 8, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, 0>, 3>(),
         make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>, LSMRC_1024_MINB>(),
         make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>, LSMRC_2048_MINB>(),
         make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>, LSMRC_4096_MINB>(),

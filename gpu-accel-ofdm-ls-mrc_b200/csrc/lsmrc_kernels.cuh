@@ -79,6 +79,10 @@ struct KernelParams {
     // value when this launch starts; a CTA's next item is atomicAdd(ticket) - ticket_base
     unsigned long long* ticket;
     unsigned long long ticket_base;
+    // data kernel, plans without the Hconj ring: antennas of one (frame, symbol) are split over
+    // ant_split teams of the CTA (power of two, <= TEAMS) whose partial sums are added in shared
+    // memory -- used when there are too few (frame, symbol) pairs to fill the GPU (latency configs)
+    int ant_split;
     const float2* pilot_bin;  // X in FFT-bin order, K entries (bin k+1 at index k)
     // outputs of MODE_DATA
     float2* combined;  // [F][n_sym_work][K], ascending frequency
@@ -492,7 +496,10 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         }
         const int groups = (p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS;
         const long long n_work = (long long)p.n_frames * p.n_sym_work;
-        const int n_items = PL::H_RING ? p.n_frames * groups : (int)((n_work + PL::TEAMS - 1) / PL::TEAMS);
+        const int AS = PL::H_RING ? 1 : p.ant_split;     // teams sharing one (frame, symbol)
+        const int slots = PL::TEAMS / AS;                // (frame, symbol) pairs per work item
+        const int aj = team % AS;                        // this team's antenna slice
+        const int n_items = PL::H_RING ? p.n_frames * groups : (int)((n_work + slots - 1) / slots);
         int rows_done = 0;  // ring rows consumed by this CTA so far
 
         // producer side of the ring: refill the stage of ring row R with Hconj row `row` of `src`
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             valid = s < p.n_sym_work;
             if (!valid) s = p.n_sym_work - 1;
         } else {
-            long long work = (long long)item * PL::TEAMS + team;
+            long long work = (long long)item * slots + team / AS;
             valid = work < n_work;
             if (!valid) work = n_work - 1;
             f = (int)(work / p.n_sym_work);
@@ -551,8 +558,13 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 #pragma unroll
             for (int n1 = 0; n1 < P; n1 += 2) v[n1] = ld_stream(x0 + n1 * T + t);
         }
-        for (int a = 0; a < p.n_ant; ++a) {
-            float2* tile = my_tiles + (PL::NBUF == 2 ? (a & 1) * PL::TILE : 0);
+        const int n_rounds = (p.n_ant + AS - 1) / AS;
+        for (int rd = 0; rd < n_rounds; ++rd) {
+            // antenna of this round; teams whose slice has run out redo the last antenna and drop the result
+            const int a_raw = rd * AS + aj;
+            const bool a_ok = a_raw < p.n_ant;
+            const int a = a_ok ? a_raw : p.n_ant - 1;
+            float2* tile = my_tiles + (PL::NBUF == 2 ? (rd & 1) * PL::TILE : 0);
             const float2* hw_row = hw_frame + (long long)a * N;
             if constexpr (PL::H_RING) {
                 const int r = a + PL::H_AHEAD;
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             }
             const float2* x_next = nullptr;
             if (PL::REG_PF != 0) {
-                if (a + 1 < p.n_ant) x_next = x0 + (long long)(a + 1) * p.ant_stride;
+                if (a + AS < p.n_ant) x_next = x0 + (long long)(a + AS) * p.ant_stride;
             }
             if (PL::REG_PF == 0) {
                 row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
@@ -571,9 +583,10 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 #pragma unroll
                 for (int n1 = 1; n1 < P; n1 += 2) v[n1] = ld_stream(xr + n1 * T + t);
             }
-            if (PF_X > 0 && a + PF_X < p.n_ant)
-                prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X) * p.ant_stride, N, t);
-            if (!PL::H_RING && PF_H > 0 && a + PF_H < p.n_ant) prefetch_row<T, true>(hw_row + (long long)PF_H * N, N, t);
+            if (PF_X > 0 && a + PF_X * AS < p.n_ant)
+                prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X * AS) * p.ant_stride, N, t);
+            if (!PL::H_RING && PF_H > 0 && a + PF_H * AS < p.n_ant)
+                prefetch_row<T, true>(hw_row + (long long)PF_H * AS * N, N, t);
             const int R = rows_done + a;
             const int st = R % PL::H_STAGES;
             const float2* h_src = PL::H_RING ? (s_hring + st * N) : hw_row;
@@ -603,7 +616,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 #else
                                 const float2 h = __ldg(h_src + bin);
 #endif
-                                acc[sl] = cmac(acc[sl], h, y);
+                                if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
                         PL::TW_REGS ? twr : nullptr);
@@ -613,6 +626,22 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             }
         }
         rows_done += p.n_ant;
+        if (AS > 1) {
+            // add the antenna slices: slice 0 of every pair sums the others in fixed order
+            float2* red = s_tiles;  // [TEAMS][P*T], aliases the tiles (all teams are past their last row)
+            __syncthreads();
+#pragma unroll
+            for (int sl = 0; sl < P; ++sl) red[(team * P + sl) * T + t] = acc[sl];
+            __syncthreads();
+            if (aj == 0) {
+                for (int jj = 1; jj < AS; ++jj) {
+#pragma unroll
+                    for (int sl = 0; sl < P; ++sl) acc[sl] = cadd(acc[sl], red[((team + jj) * P + sl) * T + t]);
+                }
+            }
+            __syncthreads();
+            valid = valid && (aj == 0);
+        }
 
         // epilogue: normalise (cpuLS.hpp:364-367), reorder (cpuLS.hpp:135-149), demap, pack.
         // Specialised on the QAM order so the demapper and the bit packing are straight-line code.

@@ -1,3 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/quick_bench.py --config c5 --frames 1 --iters 5 2>&1 | tail -2
+python tools/quick_bench.py --config c5 --frames 8192 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c1 --frames 1 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c3 --frames 1 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c4 --frames 1 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c2 --frames 256 --iters 4 2>&1 | tail -1
