@@ -59,6 +59,7 @@ ABI = {
     "lsmrc_sync": (c_int, [c_void_p]),
     "lsmrc_set_timing": (c_int, [c_void_p, c_int]),
     "lsmrc_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
+    "lsmrc_kernel_ms_history": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_int)]),
     "lsmrc_launch_count": (c_longlong, [c_void_p]),
     "lsmrc_describe_plan": (c_int, [c_void_p, c_char_p, c_size_t]),
 }
@@ -258,6 +259,13 @@ class LsMrcReceiver:
         a, b = c_float(), c_float()
         self._ck(self.lib.lsmrc_last_kernel_ms(self.h, byref(a), byref(b)))
         return a.value, b.value
+
+    def kernel_ms_history(self, max_n=256):
+        a = (c_float * max_n)()
+        b = (c_float * max_n)()
+        n = c_int()
+        self._ck(self.lib.lsmrc_kernel_ms_history(self.h, max_n, a, b, byref(n)))
+        return list(a[:n.value]), list(b[:n.value])
 
     def launch_count(self):
         return int(self.lib.lsmrc_launch_count(self.h))

@@ -282,8 +282,9 @@ struct lsmrc_ctx {
     bool have_channel = false;
     std::vector<Lane> lanes;
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    bool ev_valid = false;
+    static constexpr int kEvRing = 256;          // timed calls remembered for lsmrc_kernel_ms_history
+    cudaEvent_t ev[kEvRing][3] = {};             // [call % kEvRing] -> {start, after pilot, after data}
+    long long ev_calls = 0;                      // timed calls so far
     long long launches = 0;
     std::string err;
 };
@@ -415,17 +416,18 @@ int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frame
     p.n_frames = n_frames;
     p.combined = d_comb;
     p.bits = d_bits;
-    if (timed) CK(h, cudaEventRecord(h->ev0, st));
+    cudaEvent_t* ev = h->ev[h->ev_calls % lsmrc_ctx::kEvRing];
+    if (timed) CK(h, cudaEventRecord(ev[0], st));
     int rc = launch_pilot(h, st, p, ch, d_hconj, d_hsqrd);
     if (rc != LSMRC_OK) return rc;
-    if (timed) CK(h, cudaEventRecord(h->ev1, st));
+    if (timed) CK(h, cudaEventRecord(ev[1], st));
     if (h->cfg.n_sym > 1) {
         rc = launch_data(h, st, p, ch, d_hsqrd, 1, h->cfg.n_sym - 1);
         if (rc != LSMRC_OK) return rc;
     }
     if (timed) {
-        CK(h, cudaEventRecord(h->ev2, st));
-        h->ev_valid = true;
+        CK(h, cudaEventRecord(ev[2], st));
+        h->ev_calls++;
     }
     return LSMRC_OK;
 }
@@ -643,8 +645,9 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
         h->max_data_ctas = per_sm * prop.multiProcessorCount;
     }
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(h, e, "cudaStreamCreate"); return bail(LSMRC_ERR_CUDA); }
-    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
-        (e = cudaEventCreate(&h->ev2)) != cudaSuccess) { fail_cuda(h, e, "cudaEventCreate"); return bail(LSMRC_ERR_CUDA); }
+    for (int i = 0; i < lsmrc_ctx::kEvRing; ++i)
+        for (int j = 0; j < 3; ++j)
+            if ((e = cudaEventCreate(&h->ev[i][j])) != cudaSuccess) { fail_cuda(h, e, "cudaEventCreate"); return bail(LSMRC_ERR_CUDA); }
     std::vector<float2> tw((size_t)ops->twn);
     ops->fill_twiddles(tw.data());
     if ((e = cudaMalloc(&h->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc twiddles"); return bail(LSMRC_ERR_CUDA); }
@@ -671,9 +674,9 @@ int lsmrc_destroy(lsmrc_handle h)
     cudaFreeHost(h->h_one_sym);
     cudaFreeHost(h->h_one_comb);
     cudaFreeHost(h->h_one_bits);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->ev2) cudaEventDestroy(h->ev2);
+    for (int i = 0; i < lsmrc_ctx::kEvRing; ++i)
+        for (int j = 0; j < 3; ++j)
+            if (h->ev[i][j]) cudaEventDestroy(h->ev[i][j]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
     delete h;
@@ -1116,17 +1119,29 @@ int lsmrc_set_timing(lsmrc_handle h, int enabled)
     h->timing = enabled != 0;
     return LSMRC_OK;
 }
+int lsmrc_kernel_ms_history(lsmrc_handle h, int max_n, float* pilot_ms, float* data_ms, int* n_out)
+{
+    if (!h || max_n < 0 || !n_out) return LSMRC_ERR_INVALID;
+    long long n = h->ev_calls < lsmrc_ctx::kEvRing ? h->ev_calls : lsmrc_ctx::kEvRing;
+    if (n > max_n) n = max_n;
+    for (long long i = 0; i < n; ++i) {
+        cudaEvent_t* ev = h->ev[(h->ev_calls - n + i) % lsmrc_ctx::kEvRing];
+        CK(h, cudaEventSynchronize(ev[2]));
+        float a = 0.f, b = 0.f;
+        CK(h, cudaEventElapsedTime(&a, ev[0], ev[1]));
+        CK(h, cudaEventElapsedTime(&b, ev[1], ev[2]));
+        if (pilot_ms) pilot_ms[i] = a;
+        if (data_ms) data_ms[i] = b;
+    }
+    *n_out = (int)n;
+    return LSMRC_OK;
+}
 int lsmrc_last_kernel_ms(lsmrc_handle h, float* pilot_ms, float* data_ms)
 {
     if (!h) return LSMRC_ERR_INVALID;
-    if (!h->ev_valid) return fail(h, LSMRC_ERR_STATE, "no timed call yet (lsmrc_set_timing)");
-    CK(h, cudaEventSynchronize(h->ev2));
-    float a = 0.f, b = 0.f;
-    CK(h, cudaEventElapsedTime(&a, h->ev0, h->ev1));
-    CK(h, cudaEventElapsedTime(&b, h->ev1, h->ev2));
-    if (pilot_ms) *pilot_ms = a;
-    if (data_ms) *data_ms = b;
-    return LSMRC_OK;
+    if (h->ev_calls == 0) return fail(h, LSMRC_ERR_STATE, "no timed call yet (lsmrc_set_timing)");
+    int n = 0;
+    return lsmrc_kernel_ms_history(h, 1, pilot_ms, data_ms, &n);
 }
 long long lsmrc_launch_count(lsmrc_handle h) { return h ? h->launches : 0; }
 int lsmrc_describe_plan(lsmrc_handle h, char* buf, size_t buf_len)

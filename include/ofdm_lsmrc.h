@@ -167,6 +167,9 @@ int lsmrc_sync(lsmrc_handle h);
  * call (waits for them).  Enable with lsmrc_set_timing(h, 1); off by default. */
 int lsmrc_set_timing(lsmrc_handle h, int enabled);
 int lsmrc_last_kernel_ms(lsmrc_handle h, float *pilot_ms, float *data_ms);
+/* the same for the most recent min(max_n, 256) timed calls, oldest first; waits for them.  Lets a
+ * benchmark read per-kernel durations of a whole timed region without a sync inside it. */
+int lsmrc_kernel_ms_history(lsmrc_handle h, int max_n, float *pilot_ms, float *data_ms, int *n_out);
 /* number of kernels this library has launched through handle h since creation */
 long long lsmrc_launch_count(lsmrc_handle h);
 /* plan description, e.g. "N=1024 P=32 R2=32 R3=1 teams=4 threads=128 smem=75512" */
