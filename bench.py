@@ -253,7 +253,7 @@ def other_configs_leg(m, dev_index, peak):
 
     out = {}
     dev = torch.device("cuda", dev_index)
-    for name, frames in (("c1", 16384), ("c3", 192), ("c4", 48)):
+    for name, frames in (("c1", 16384), ("c3", 384), ("c4", 192)):
         cfg = m.CONFIGS[name]
         rx = torch.randn((frames, cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len, 2), device=dev)
         comb = torch.empty((frames, cfg.n_sym - 1, cfg.K, 2), device=dev)

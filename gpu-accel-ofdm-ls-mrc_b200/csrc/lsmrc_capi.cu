@@ -29,7 +29,7 @@ struct PlanOps {
     int N, P, R2, R3, teams, threads, twn, minb;
     size_t smem;
     void (*fill_twiddles)(float2*);
-    cudaError_t (*prepare)(int* data_ctas_per_sm);
+    cudaError_t (*prepare)(int* data_ctas_per_sm, int* pilot_ctas_per_sm);
     cudaError_t (*launch)(int mode, const KernelParams&, cudaStream_t, int max_data_ctas, unsigned* grid_out, long long* items_out);
 };
 
@@ -59,7 +59,7 @@ template <class PL, int MINB>
 constexpr int pilot_minb() { return (LSMRC_PILOT_WIDE && PL::P >= 32 && MINB > 2) ? 2 : MINB; }
 
 template <class PL, int MINB>
-cudaError_t prepare_impl(int* data_ctas_per_sm)
+cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
 {
     cudaError_t e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
@@ -70,7 +70,11 @@ cudaError_t prepare_impl(int* data_ctas_per_sm)
     e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_FFT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)PL::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    // resident data-kernel CTAs per SM: the persistent grid is this times the SM count
+    // resident CTAs per SM: the persistent data grid is this times the SM count; the pilot grid is
+    // sized to at most one such wave when frames are few
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(pilot_ctas_per_sm, lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()>,
+                                                      PL::THREADS, PL::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS,
                                                          PL::SMEM_BYTES);
 }
@@ -232,7 +236,7 @@ struct ChanState {
     unsigned long long ticket_next = 0;    // host mirror: value of *ticket once all enqueued launches have run
     int frames = 0;
 };
-constexpr int kPilotCtaTarget = 296;  // pilot kernel: aim for >= 2 CTAs per SM when frames are few
+constexpr int kPilotCtaTarget = 1024;  // upper bound on frames*groups - frames (epart scratch rows)
 
 struct Lane {
     ChanState ch;
@@ -262,6 +266,7 @@ struct lsmrc_ctx {
     size_t frame_elems = 0;  // S*slot
     const PlanOps* ops = nullptr;
     int max_data_ctas = 1;  // persistent data-kernel grid: resident CTAs per SM x SM count
+    int pilot_wave = 1;     // pilot-kernel CTAs resident at once on the whole GPU
     float2* d_tw = nullptr;
     float2* d_pilot_bin = nullptr;
     bool have_pilot = false;
@@ -364,12 +369,14 @@ void free_chan(ChanState& c)
     c = ChanState();
 }
 
-// antenna groups per frame for the pilot kernel: enough CTAs to fill the GPU when frames are few
+// antenna groups per frame for the pilot kernel: when frames are fewer than one wave of resident
+// CTAs, split every frame's antennas over as many CTAs as still fit in that single wave
 int pilot_groups(const lsmrc_ctx* h, int n_frames)
 {
     const int max_g = (h->cfg.n_ant + h->ops->teams - 1) / h->ops->teams;
-    int g = (kPilotCtaTarget + n_frames - 1) / n_frames;
+    int g = h->pilot_wave / n_frames;
     if (g > max_g) g = max_g;
+    if (g > kPilotCtaTarget) g = kPilotCtaTarget;  // epart scratch is sized for frames + kPilotCtaTarget rows
     if (g < 1) g = 1;
     return g;
 }
@@ -639,10 +646,11 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
         return fail(nullptr, rc, msg);
     };
     {
-        int per_sm = 0;
-        if ((e = ops->prepare(&per_sm)) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute"); return bail(LSMRC_ERR_CUDA); }
-        if (per_sm < 1) { h->err = "data kernel does not fit on an SM"; return bail(LSMRC_ERR_CUDA); }
+        int per_sm = 0, pilot_per_sm = 0;
+        if ((e = ops->prepare(&per_sm, &pilot_per_sm)) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute"); return bail(LSMRC_ERR_CUDA); }
+        if (per_sm < 1 || pilot_per_sm < 1) { h->err = "kernel does not fit on an SM"; return bail(LSMRC_ERR_CUDA); }
         h->max_data_ctas = per_sm * prop.multiProcessorCount;
+        h->pilot_wave = pilot_per_sm * prop.multiProcessorCount;
     }
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(h, e, "cudaStreamCreate"); return bail(LSMRC_ERR_CUDA); }
     for (int i = 0; i < lsmrc_ctx::kEvRing; ++i)

@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench.json'))
-print('value %.3e  ms/step %.3f  frac %.3f  achieved %.0f GB/s  e2e %.3e  cpu %.3e' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['achieved'], d['e2e']['value'], d['cpu_baseline']['value']))
-print('clocks', d['clocks'])
-print('sustained', d['sustained'])
-PY
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python tools/quick_bench.py --config c4 --frames 48 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c4 --frames 192 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c3 --frames 384 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c5 --frames 1 --iters 4 2>&1 | tail -1
+python tools/quick_bench.py --config c2 --frames 256 --iters 4 2>&1 | tail -1
