@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python tools/quick_bench.py --config c4 --frames 48 --iters 4 2>&1 | tail -1
-python tools/quick_bench.py --config c4 --frames 192 --iters 4 2>&1 | tail -1
-python tools/quick_bench.py --config c3 --frames 384 --iters 4 2>&1 | tail -1
-python tools/quick_bench.py --config c5 --frames 1 --iters 4 2>&1 | tail -1
-python tools/quick_bench.py --config c2 --frames 256 --iters 4 2>&1 | tail -1
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
+$CMD > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+echo "launch list rc=$?"; grep -c lsmrc gpurun_out/launches.csv

@@ -31,7 +31,7 @@ tot = sum(a[1] for a in agg.values())
 tot_ours = sum(v for _, _, v in ours)
 with open(os.path.join(out_dir, f"{tag}_launch_list.md"), "w") as f:
     f.write(f"# {tag}: ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e`\n\n")
-    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare shares).\n")
+    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 1500` (cold-cache, serialised: compare shares).\n")
     f.write("torch kernels below are the synthetic-input generator, outside the timed region; inside the timed region only\n"
             "the two `lsmrc_kernel` instantiations launch (MODE 0 = pilot, MODE 1 = data).\n\n")
     f.write("| launches | total us | share of all | avg us | kernel |\n|---|---|---|---|---|\n")
@@ -55,7 +55,7 @@ for sec in (0, 1):
                           capture_output=True, text=True).stdout + "\n"
 with open(os.path.join(out_dir, f"{tag}_ncu_full_summary.txt"), "w") as f:
     f.write(f"{tag}: ncu --set full --clock-control none --import-source on -k regex:lsmrc_kernel -s 8 -c 2 python bench.py --steps 3 --warmup 3 ...\n")
-    f.write("(c2, 64 frames per launch; numbers under the profiler are not bench values)\n\n")
+    f.write("(c2, 256 frames per launch; numbers under the profiler are not bench values)\n\n")
     f.write(summ)
     f.write("\n---- top stall instructions (SASS) ----\n")
     f.write(hot)
@@ -73,10 +73,11 @@ for r in rr[2:]:
         v = float(d[key])
         u = units[h.index(key)].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
-    name = d["Kernel Name"]
-    is_data = int(d["Grid Size"].strip("()").split(",")[0]) > 1000 or "1, 3>(" in name.replace(" ", "")[-12:]
-    traffic["data" if is_data else "pilot"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-json.dump({"c2": {"frames": 64, "data_kernel_dram_bytes": traffic.get("data"), "pilot_kernel_dram_bytes": traffic.get("pilot"),
+    import re
+    mm = re.search(r">,\s*(\d),\s*\d>\(", d["Kernel Name"])
+    mode = int(mm.group(1)) if mm else -1
+    traffic["data" if mode == 1 else "pilot"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+json.dump({"c2": {"frames": 256, "data_kernel_dram_bytes": traffic.get("data"), "pilot_kernel_dram_bytes": traffic.get("pilot"),
                   "source": f"profiles/{tag}_ncu_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}},
           open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, "traffic.json")).read())
