@@ -22,6 +22,11 @@ CASES = {
     "cp0": (4, 64, 0, 16, 2, 2),
     "odd_ant": (7, 1024, 72, 3, 4, 2),
     "one_ant": (1, 1024, 64, 3, 2, 1),
+    "one_data_symbol": (6, 1024, 64, 2, 4, 3),      # S-1 = 1: three of the four teams of a CTA idle
+    "odd_cp": (4, 64, 7, 5, 2, 3),                  # rows start 8-byte but not 16-byte aligned
+    "odd_cp_1024": (3, 1024, 9, 3, 6, 2),
+    "many_frames_small": (2, 128, 4, 3, 4, 300),    # several persistent rounds per CTA
+    "syms_not_multiple_of_teams": (4, 1024, 64, 8, 2, 2),  # 7 data symbols, 4 teams per CTA
 }
 SNR = {2: 10.0, 4: 15.0, 6: 20.0}
 
