@@ -326,11 +326,29 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
 #pragma unroll
             for (int k2 = 0; k2 < R2; ++k2) sink(i * R2 + k2, b + (PL::N / R2) * k2, u[brev<R2>(k2)]);
         } else {
+            // second-level twiddles W_T^(m2*k2): same chunk-ahead fetch as the first level
+            constexpr int C2 = (R2 >= 8) ? PL::TW_CHUNK : R2;
+            float2 wa[C2], wb[C2];
 #pragma unroll
-            for (int k2 = 0; k2 < R2; ++k2) {
-                float2 val = u[brev<R2>(k2)];
-                if (k2 > 0) val = cmul(val, s_tw2[(k2 - 1) * R3 + m2]);
-                col[k2 * R3] = val;
+            for (int j = 0; j < C2; ++j) wa[j] = (j == 0) ? make_float2(1.f, 0.f) : lds_volatile(s_tw2 + (j - 1) * R3 + m2);
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < R2 / C2; ++c) {
+                if (c + 1 < R2 / C2) {
+#pragma unroll
+                    for (int j = 0; j < C2; ++j) wb[j] = lds_volatile(s_tw2 + ((c + 1) * C2 + j - 1) * R3 + m2);
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < C2; ++j) {
+                    const int k2 = c * C2 + j;
+                    float2 val = u[brev<R2>(k2)];
+                    if (k2 > 0) val = cmul(val, wa[j]);
+                    col[k2 * R3] = val;
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < C2; ++j) wa[j] = wb[j];
             }
         }
     }
