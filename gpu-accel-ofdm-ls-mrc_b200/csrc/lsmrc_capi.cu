@@ -179,7 +179,7 @@ PlanOps make_ops()
 #define LSMRC_2048_NBUF 1
 #endif
 #ifndef LSMRC_2048_PFX
-#define LSMRC_2048_PFX 0
+#define LSMRC_2048_PFX 1
 #endif
 #ifndef LSMRC_2048_PFH
 #define LSMRC_2048_PFH 0
@@ -197,7 +197,7 @@ PlanOps make_ops()
 #define LSMRC_4096_NBUF 1
 #endif
 #ifndef LSMRC_4096_PFX
-#define LSMRC_4096_PFX 0
+#define LSMRC_4096_PFX 1
 #endif
 #ifndef LSMRC_4096_PFH
 #define LSMRC_4096_PFH 0
@@ -236,7 +236,7 @@ struct ChanState {
     unsigned long long ticket_next = 0;    // host mirror: value of *ticket once all enqueued launches have run
     int frames = 0;
 };
-constexpr int kPilotCtaTarget = 1024;  // upper bound on frames*groups - frames (epart scratch rows)
+constexpr int kPilotCtaTarget = 4096;  // upper bound on frames*groups - frames (epart scratch rows)
 
 struct Lane {
     ChanState ch;
@@ -369,14 +369,21 @@ void free_chan(ChanState& c)
     c = ChanState();
 }
 
-// antenna groups per frame for the pilot kernel: when frames are fewer than one wave of resident
-// CTAs, split every frame's antennas over as many CTAs as still fit in that single wave
+// antenna groups per frame for the pilot kernel: aim for about two waves of resident CTAs so that
+// the GPU is filled and the tail is short (cross-CTA energy sums are combined by the last CTA of
+// each frame), but keep >= 16 rows per team so the per-CTA setup (twiddles, pilot reciprocals) stays
+// amortised -- unless the launch is tiny (latency configs), where every antenna gets its own team
 int pilot_groups(const lsmrc_ctx* h, int n_frames)
 {
-    const int max_g = (h->cfg.n_ant + h->ops->teams - 1) / h->ops->teams;
-    int g = h->pilot_wave / n_frames;
+    const int teams = h->ops->teams;
+    const int max_g = (h->cfg.n_ant + teams - 1) / teams;
+    const int min_rows = ((long long)n_frames * 4 >= h->pilot_wave) ? 16 : 1;
+    int g_rows = h->cfg.n_ant / (teams * min_rows);
+    if (g_rows < 1) g_rows = 1;
+    int g = (2 * h->pilot_wave + n_frames - 1) / n_frames;
+    if (g > g_rows) g = g_rows;
     if (g > max_g) g = max_g;
-    if (g > kPilotCtaTarget) g = kPilotCtaTarget;  // epart scratch is sized for frames + kPilotCtaTarget rows
+    if ((long long)g * n_frames > (long long)n_frames + kPilotCtaTarget) g = (int)(((long long)n_frames + kPilotCtaTarget) / n_frames);
     if (g < 1) g = 1;
     return g;
 }

@@ -436,6 +436,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
             float2 v[P];
             row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
+            if (a_raw + per_iter < p.n_ant)  // this team's next antenna: pull its row into L2 meanwhile
+                prefetch_row<T, false>(x0 + (long long)(a_raw + per_iter) * p.ant_stride, N, t);
             row_fft<PL>(v, nullptr, tile, s_tw1, s_tw2, t, team,
                         [&](int sl, int bin, float2 z) {
                             // LS estimate, complex division of cpuLS.hpp:233-244, then conj (:303-307)
