@@ -275,6 +275,44 @@ def other_configs_leg(m, dev_index, peak):
     return out
 
 
+def frontend_leg(m, dev_index, peak):
+    """the front end that precedes the hot path (rx_and_corr.cpp:332-393) on the GPU: PN frame sync over a whole
+    c2-sized capture and the stitching of the frame into the receiver's input layout"""
+    import torch
+
+    cfg = m.CONFIGS["c2"]
+    dev = torch.device("cuda", dev_index)
+    L = 255
+    samps = L + cfg.n_sym * (cfg.fft_size + cfg.cp_len) + 512
+    b1 = 0.05 * torch.randn((cfg.n_ant, samps, 2), device=dev)
+    b2 = 0.05 * torch.randn((cfg.n_ant, samps, 2), device=dev)
+    pn = torch.view_as_real(torch.from_numpy(m.synth.make_pn()).to(dev)).contiguous()
+    b1[:, 300:300 + L, 0] = pn[:, 0]
+    b1[:, 300:300 + L, 1] = 0
+    rx = torch.empty((cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len, 2), device=dev)
+    with m.LsMrcReceiver.from_config(cfg, device=dev_index) as r:
+        stream = torch.cuda.current_stream(dev)
+        r.set_stream(stream.cuda_stream)
+        for _ in range(3):
+            off = r.sync_correlate(b1, cfg.n_ant, samps, pn, L, 0.5)[0]
+            r.sync_assemble(b1, b2, samps, max(off, 0), L, rx)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(stream)
+        for _ in range(10):
+            off = r.sync_correlate(b1, cfg.n_ant, samps, pn, L, 0.5)[0]
+        e[1].record(stream)
+        for _ in range(10):
+            r.sync_assemble(b1, b2, samps, off, L, rx)
+        e[2].record(stream)
+        torch.cuda.synchronize(dev)
+    t_corr, t_asm = e[0].elapsed_time(e[1]) / 10, e[1].elapsed_time(e[2]) / 10
+    taps = cfg.n_ant * (samps - L + 1) * L
+    return {"workload": f"c2 capture: {cfg.n_ant} channels x {samps} samples, PN 255", "offset_found": off,
+            "correlate_ms": t_corr, "correlate_gmac_per_s": taps / (t_corr * 1e-3) / 1e9,
+            "assemble_ms": t_asm, "assemble_gbs": 2 * rx.numel() * 4 / (t_asm * 1e-3) / 1e9,
+            "assemble_frac_of_hbm_peak": 2 * rx.numel() * 4 / (t_asm * 1e-3) / 1e9 / peak}
+
+
 def workload_config(cfg, frames, e2e_frames):
     return {"workload": f"{cfg.name}: {cfg.fft_size}-pt FFT, CP {cfg.cp_len}, {cfg.n_ant} antennas, 1 pilot + "
                         f"{cfg.n_sym - 1} data symbols, {1 << cfg.qam_bits}-QAM",
@@ -424,12 +462,13 @@ def main():
         sustained = {"steps": n_long, "measured_over_last": len(dl), "data_kernel_ms": dms, "achieved": ach, "frac": ach / peak,
                      "value": F * cfg.antenna_samples_per_frame / ((dms + statistics.mean(pl)) * 1e-3), "clocks": ck2}
 
-    latency = others = None
+    latency = others = frontend = None
     if rank == 0 and world == 1 and not args.no_extras:
         del rx, rx_f, comb, bits
         torch.cuda.empty_cache()
         latency = latency_leg(m, local)
         others = other_configs_leg(m, local, peak)
+        frontend = frontend_leg(m, local, peak)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -437,7 +476,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, F, Fe), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks, "plan": rcv.describe_plan(), "latency": latency,
-                "sustained": sustained, "other_configs": others,
+                "sustained": sustained, "other_configs": others, "frontend": frontend,
                 "parity": {"bit_errors_vs_source": bit_errors, "ber": ber, "frames_checked": 2}}
         print(json.dumps(line), flush=True)
     rcv.close()

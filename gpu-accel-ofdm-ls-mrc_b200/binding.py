@@ -47,6 +47,9 @@ ABI = {
     "lsmrc_stage_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "lsmrc_stage_shift_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong]),
     "lsmrc_copy_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "lsmrc_sync_correlate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_float, POINTER(c_int), POINTER(c_int),
+                                     POINTER(c_float), c_void_p]),
+    "lsmrc_sync_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lsmrc_dev_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "lsmrc_dev_free": (c_int, [c_void_p, c_void_p]),
     "lsmrc_copy_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
@@ -223,6 +226,16 @@ class LsMrcReceiver:
     def stage(self, name, *args):
         fn = getattr(self.lib, "lsmrc_stage_" + name)
         self._ck(fn(self.h, *[_ptr(a) for a in args]))
+
+    # -- receive front end (device tensors)
+    def sync_correlate(self, d_buf, n_chan, samps, d_pn, pn_len, thres, d_metric_all=None):
+        off, ch, m = c_int(), c_int(), c_float()
+        self._ck(self.lib.lsmrc_sync_correlate(self.h, _ptr(d_buf), n_chan, samps, _ptr(d_pn), pn_len, thres, byref(off),
+                                               byref(ch), byref(m), _ptr(d_metric_all)))
+        return off.value, ch.value, m.value
+
+    def sync_assemble(self, d_buf1, d_buf2, samps, offset, pn_len, d_rx_frame):
+        self._ck(self.lib.lsmrc_sync_assemble(self.h, _ptr(d_buf1), _ptr(d_buf2), samps, offset, pn_len, _ptr(d_rx_frame)))
 
     # -- plumbing
     def host_alloc(self, nbytes):

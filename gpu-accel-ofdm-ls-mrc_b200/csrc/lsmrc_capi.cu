@@ -286,6 +286,7 @@ struct lsmrc_ctx {
     uint8_t* h_one_bits = nullptr;
     bool have_channel = false;
     std::vector<Lane> lanes;
+    unsigned long long* d_hit = nullptr;  // frame-sync first-hit key
     bool timing = false;
     static constexpr int kEvRing = 256;          // timed calls remembered for lsmrc_kernel_ms_history
     cudaEvent_t ev[kEvRing][3] = {};             // [call % kEvRing] -> {start, after pilot, after data}
@@ -679,6 +680,7 @@ int lsmrc_destroy(lsmrc_handle h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (Lane& L : h->lanes) free_lane(L);
     cudaFree(h->d_tw);
+    cudaFree(h->d_hit);
     cudaFree(h->d_pilot_bin);
     free_chan(h->dev_ch);
     free_chan(h->one_ch);
@@ -1043,6 +1045,62 @@ int lsmrc_stage_shift_rows(lsmrc_handle h, const void* d_in, void* d_out, long l
     CK(h, cudaSetDevice(h->cfg.device));
     k_shift_rows<<<ew_grid(rows * h->K), 256, 0, compute_stream(h)>>>(static_cast<const float2*>(d_in),
                                                                        static_cast<float2*>(d_out), rows, h->K);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+// ---- receive front end before the hot path (rx_and_corr.cpp:332-393) ---------------------------------------
+
+int lsmrc_sync_correlate(lsmrc_handle h, const void* d_buf, int n_chan, int samps, const void* d_pn, int pn_len,
+                         float thres, int* offset, int* chan, float* metric, void* d_metric_all)
+{
+    if (!h || !d_buf || !d_pn || !offset) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_chan < 1 || pn_len < 1 || samps < pn_len || pn_len > 4096) return fail(h, LSMRC_ERR_INVALID, "bad sizes");
+    if ((long long)n_chan * samps >= (1LL << 31)) return fail(h, LSMRC_ERR_INVALID, "capture too long");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = compute_stream(h);
+    if (!h->d_hit) CK(h, cudaMalloc(&h->d_hit, sizeof(unsigned long long)));
+    CK(h, cudaMemsetAsync(h->d_hit, 0xff, sizeof(unsigned long long), st));
+    const int n_off = samps - pn_len + 1;
+    dim3 grid((unsigned)((n_off + kSyncThreads - 1) / kSyncThreads), (unsigned)n_chan);
+    const size_t smem = sizeof(float2) * (size_t)(pn_len + kSyncThreads + pn_len - 1);
+    k_sync_correlate<<<grid, kSyncThreads, smem, st>>>(static_cast<const float2*>(d_buf), samps,
+                                                      static_cast<const float2*>(d_pn), pn_len, thres, h->d_hit,
+                                                      static_cast<float*>(d_metric_all));
+    h->launches++;
+    CK(h, cudaGetLastError());
+    unsigned long long key = 0;
+    CK(h, cudaMemcpyAsync(&key, h->d_hit, sizeof(key), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (key == ~0ULL) {
+        *offset = -1;
+        if (chan) *chan = -1;
+        if (metric) *metric = 0.f;
+        return LSMRC_OK;
+    }
+    const long long pos = (long long)(key >> 32);
+    *offset = (int)(pos % samps);
+    if (chan) *chan = (int)(pos / samps);
+    if (metric) {
+        const unsigned bits = (unsigned)(key & 0xffffffffu);
+        std::memcpy(metric, &bits, sizeof(float));
+    }
+    return LSMRC_OK;
+}
+
+int lsmrc_sync_assemble(lsmrc_handle h, const void* d_buf1, const void* d_buf2, int samps, int offset, int pn_len,
+                        void* d_rx_frame)
+{
+    if (!h || !d_buf1 || !d_buf2 || !d_rx_frame) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    const lsmrc_config& c = h->cfg;
+    const long long frame = (long long)c.n_sym * (c.fft_size + c.cp_len);
+    if (offset < 0 || pn_len < 0 || offset + pn_len > samps || (long long)samps - pn_len < frame)
+        return fail(h, LSMRC_ERR_INVALID, "capture buffer shorter than PN + one frame, or bad offset");
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_sync_assemble<<<ew_grid(frame * c.n_ant), 256, 0, compute_stream(h)>>>(
+        static_cast<const float2*>(d_buf1), static_cast<const float2*>(d_buf2), samps, offset, pn_len,
+        static_cast<float2*>(d_rx_frame), c.n_sym, c.n_ant, c.fft_size + c.cp_len);
     h->launches++;
     CK(h, cudaGetLastError());
     return LSMRC_OK;

@@ -800,4 +800,63 @@ __global__ void k_shift_rows(const float2* __restrict__ in, float2* __restrict__
     }
 }
 
+// ---- receive front end before the hot path (rx_and_corr.cpp:332-393) ----------------
+
+// PN-sequence frame sync, rx_and_corr.cpp:335-360: metric[ch][i] = |sum_j pn[j]*buf[ch][i+j]| / L for every
+// channel and offset at once (the reference scans them one by one on the CPU and stops at the first hit).
+// The first hit in the reference's scan order (channel-major, offset ascending) is the minimum of
+// key = (ch*samps + i) << 32 | float_bits(metric) over all positions with metric >= thres.
+// Products and sums are rounded separately in tap order, exactly as the (un-contracted) CPU loop does.
+constexpr int kSyncThreads = 256;
+__global__ void __launch_bounds__(kSyncThreads) k_sync_correlate(const float2* __restrict__ buf, int samps,
+                                                                  const float2* __restrict__ pn, int L, float thres,
+                                                                  unsigned long long* __restrict__ first_hit,
+                                                                  float* __restrict__ metric_all)
+{
+    extern __shared__ float2 s_sync[];  // [L] pn, then [kSyncThreads + L - 1] samples
+    float2* s_pn = s_sync;
+    float2* s_x = s_sync + L;
+    const int ch = blockIdx.y;
+    const int i0 = blockIdx.x * kSyncThreads;
+    const int n_off = samps - L + 1;
+    const float2* x = buf + (long long)ch * samps;
+    for (int j = threadIdx.x; j < L; j += kSyncThreads) s_pn[j] = pn[j];
+    for (int j = threadIdx.x; j < kSyncThreads + L - 1; j += kSyncThreads)
+        s_x[j] = (i0 + j < samps) ? x[i0 + j] : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    if (i >= n_off) return;
+    float re = 0.f, im = 0.f;
+    const float2* w = s_x + threadIdx.x;
+    for (int j = 0; j < L; ++j) {
+        const float2 p = s_pn[j], v = w[j];
+        re = __fadd_rn(re, __fsub_rn(__fmul_rn(p.x, v.x), __fmul_rn(p.y, v.y)));
+        im = __fadd_rn(im, __fadd_rn(__fmul_rn(p.x, v.y), __fmul_rn(p.y, v.x)));
+    }
+    const float m = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im))), (float)L);
+    if (metric_all) metric_all[(long long)ch * samps + i] = m;
+    if (m >= thres) {
+        const unsigned long long key = ((unsigned long long)((long long)ch * samps + i) << 32) | (unsigned long long)__float_as_uint(m);
+        atomicMin(first_hit, key);
+    }
+}
+
+// Frame stitching + slot gather, rx_and_corr.cpp:372-393 and :64-87 in one pass: the frame starts right
+// after the PN sequence at buf1[ch][off+L] and wraps into buf2; rx[s][a][n] = frame[a][s*(N+C) + n] with the
+// cyclic prefix left in (the fused kernels strip it).
+__global__ void k_sync_assemble(const float2* __restrict__ buf1, const float2* __restrict__ buf2, int samps, int off,
+                                int L, float2* __restrict__ rx, int S, int A, int row)
+{
+    const long long total = (long long)S * A * row;
+    const int n_first = samps - off - L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % row);
+        const long long sa = i / row;
+        const int a = (int)(sa % A);
+        const int s = (int)(sa / A);
+        const int m = s * row + n;
+        rx[i] = (m < n_first) ? buf1[(long long)a * samps + off + L + m] : buf2[(long long)a * samps + (m - n_first)];
+    }
+}
+
 }  // namespace lsmrc

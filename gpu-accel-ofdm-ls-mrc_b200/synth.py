@@ -128,3 +128,37 @@ def make_frames_torch(n_frames, cfg, device, seed=None, snr_db="cfg", chunk=64):
             rx[f0:f0 + nf, :, :, :C] = yt[..., N - C:]
         del tx, h, hr, yt, idx
     return rx, pilot_asc, src
+
+
+def make_pn(length=255, seed=0x1D):
+    """+-1 maximal-length sequence (8-bit LFSR x^8+x^6+x^5+x^4+1 -> period 255), as complex64.  Stands in for
+    the reference's PNSeq_255_MaxLenSeq.dat (rx_and_corr.cpp:228), which is not shipped."""
+    reg = seed & 0xFF or 1
+    out = np.empty(length, np.float32)
+    for i in range(length):
+        out[i] = 1.0 if (reg & 1) else -1.0
+        fb = ((reg >> 0) ^ (reg >> 2) ^ (reg >> 3) ^ (reg >> 4)) & 1
+        reg = (reg >> 1) | (fb << 7)
+    return out.astype(np.complex64)
+
+
+def make_capture(rx_frame, pn, offset, samps=None, noise=0.02, seed=0):
+    """Wrap one frame [S][A][N+C] into the two per-channel capture buffers the reference's receive loop sees
+    (rx_and_corr.cpp:305-312): noise, then conj(pn) starting at `offset` of buffer 1 (the correlator multiplies by
+    pn without conjugating, :348), then the frame, whose tail wraps into buffer 2.  Returns (buf1, buf2) [A][samps]."""
+    S, A, row = rx_frame.shape
+    L = pn.shape[0]
+    frame = np.ascontiguousarray(np.transpose(rx_frame, (1, 0, 2))).reshape(A, S * row)   # [A][S*row]
+    samps = samps or (L + S * row)
+    assert samps - L >= S * row and 0 <= offset and offset + L <= samps
+    rng = np.random.default_rng(seed)
+    scale = float(np.abs(frame).mean()) or 1.0
+    def noise_buf():
+        return (noise * scale * (rng.standard_normal((A, samps)) + 1j * rng.standard_normal((A, samps)))).astype(np.complex64)
+    buf1, buf2 = noise_buf(), noise_buf()
+    buf1[:, offset:offset + L] = np.conj(pn)[None, :]
+    n_first = samps - offset - L
+    stream = np.concatenate([frame, noise_buf()[:, :max(0, samps - L - S * row)]], axis=1)  # samps-L per channel
+    buf1[:, offset + L:] = stream[:, :n_first]
+    buf2[:, :offset] = stream[:, n_first:n_first + offset]
+    return buf1, buf2

@@ -149,6 +149,19 @@ int lsmrc_stage_combine(lsmrc_handle h, const void *d_yf, const void *d_hsqrd, v
 int lsmrc_stage_shift_rows(lsmrc_handle h, const void *d_in, void *d_out, long long rows);
 int lsmrc_copy_device(lsmrc_handle h, void *d_dst, const void *d_src, size_t bytes); /* D2D on the compute stream */
 
+/* ---- receive front end before the hot path: frame sync and frame stitching of
+ *      rx_and_corr.cpp:332-393 + the slot gather of :64-87, on the GPU, so a capture that is already in
+ *      device memory never goes back through the CPU correlator and the shm ring. ------------------------ */
+/* PN correlator (rx_and_corr.cpp:335-360): metric[ch][i] = |sum_j pn[j]*buf[ch][i+j]| / pn_len over
+ * d_buf [n_chan][samps]; *offset = first i (channels scanned in order) with metric >= thres, or -1.
+ * d_metric_all (device, [n_chan][samps] float) is optional.  Synchronous. */
+int lsmrc_sync_correlate(lsmrc_handle h, const void *d_buf, int n_chan, int samps, const void *d_pn, int pn_len,
+                         float thres, int *offset, int *chan, float *metric, void *d_metric_all);
+/* Stitch one frame that starts at buf1[ch][offset + pn_len] and wraps into buf2 (rx_and_corr.cpp:372-393)
+ * straight into the hot path's input layout [S][A][N+C] (CP left in).  Buffers are [A][samps]. */
+int lsmrc_sync_assemble(lsmrc_handle h, const void *d_buf1, const void *d_buf2, int samps, int offset, int pn_len,
+                        void *d_rx_frame);
+
 /* ---- memory and stream plumbing, so callers need no CUDA headers (replaces the raw
  *      cudaMalloc/cudaMemcpy/cudaFree calls of gpuLS_main.cu:73-91,135-139) ------------ */
 int lsmrc_dev_alloc(lsmrc_handle h, size_t bytes, void **d_ptr);

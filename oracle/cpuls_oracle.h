@@ -52,6 +52,14 @@ int oracle_demod_frames(const oc_complex *rx, const oc_complex *pilot_asc, int F
                         int N, int C, int qam_bits, oc_complex *hconj, float *hsqrd,
                         oc_complex *combined, uint8_t *bits, int n_threads);
 
+/* receive front end before the hot path (rxsync_oracle.c; rx_and_corr.cpp:64-87,332-393) */
+int oracle_sync_correlate(const oc_complex *buf, int A, int samps, const oc_complex *pn, int L, float thres,
+                          int *ch_out, float *metric_out, float *metric_all);
+void oracle_sync_assemble(const oc_complex *buf1, const oc_complex *buf2, int A, int samps, int off, int L,
+                          oc_complex *copy_buff);
+void oracle_sync_to_slots(const oc_complex *copy_buff, int A, int per_chan, int S, int N, int cp, int keep_cp,
+                          oc_complex *slots);
+
 #ifdef __cplusplus
 }
 #endif

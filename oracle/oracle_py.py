@@ -49,6 +49,14 @@ def _lib(fast: bool = False) -> ctypes.CDLL:
         lib.oracle_demap_row.restype = None
         lib.oracle_demap_row.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_sync_correlate.restype = ctypes.c_int
+        lib.oracle_sync_correlate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_sync_assemble.restype = None
+        lib.oracle_sync_assemble.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_void_p]
+        lib.oracle_sync_to_slots.restype = None
+        lib.oracle_sync_to_slots.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]
         _LIBS[name] = lib
     return _LIBS[name]
 
@@ -138,3 +146,33 @@ def run_reference(rx: np.ndarray, pilot_asc, cp: int):
         hsqrd = np.fromfile(os.path.join(d, "out.hsqrd"), np.float32).reshape(F, K)
         comb = np.fromfile(os.path.join(d, "out.comb"), np.complex64).reshape(F, S - 1, K)
     return {"hconj": hconj, "hsqrd": hsqrd, "combined": comb}
+
+
+# ---- receive front end (rxsync_oracle.c) ------------------------------------------------------------
+def sync_correlate(buf: np.ndarray, pn: np.ndarray, thres: float, want_all: bool = False):
+    """buf [A][samps] c64, pn [L] c64 -> (offset or -1, channel, metric[, metric_all [A][samps]])"""
+    buf = np.ascontiguousarray(buf, np.complex64)
+    pn = np.ascontiguousarray(pn, np.complex64)
+    A, samps = buf.shape
+    ch, m = ctypes.c_int(-1), ctypes.c_float(0)
+    allm = np.zeros((A, samps), np.float32) if want_all else None
+    off = _lib().oracle_sync_correlate(buf.ctypes.data, A, samps, pn.ctypes.data, pn.shape[0], thres, ctypes.byref(ch),
+                                       ctypes.byref(m), allm.ctypes.data if want_all else None)
+    return (off, ch.value, m.value, allm) if want_all else (off, ch.value, m.value)
+
+
+def sync_assemble(buf1: np.ndarray, buf2: np.ndarray, off: int, pn_len: int) -> np.ndarray:
+    buf1 = np.ascontiguousarray(buf1, np.complex64)
+    buf2 = np.ascontiguousarray(buf2, np.complex64)
+    A, samps = buf1.shape
+    out = np.empty((A, samps - pn_len), np.complex64)
+    _lib().oracle_sync_assemble(buf1.ctypes.data, buf2.ctypes.data, A, samps, off, pn_len, out.ctypes.data)
+    return out
+
+
+def sync_to_slots(copy_buff: np.ndarray, S: int, N: int, cp: int, keep_cp: bool) -> np.ndarray:
+    copy_buff = np.ascontiguousarray(copy_buff, np.complex64)
+    A, per = copy_buff.shape
+    out = np.empty((S, A, N + (cp if keep_cp else 0)), np.complex64)
+    _lib().oracle_sync_to_slots(copy_buff.ctypes.data, A, per, S, N, cp, int(keep_cp), out.ctypes.data)
+    return out

@@ -56,7 +56,7 @@ def test_host_programs_build_without_cuda_headers(ofdm):
     ofdm.load_library()  # make sure the .so the programs link exists
     r = subprocess.run(["make", "-C", HOST, "--no-print-directory"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    for exe in ("gpuLS_main", "ring_feeder", "stream_main"):
+    for exe in ("gpuLS_main", "ring_feeder", "stream_main", "rx_and_corr_gpu"):
         assert os.path.exists(os.path.join(HOST, "bin", exe))
     # the facade keeps the reference's names (gpuLS.cuh:72-113, gpuLS_main.cu:104-141)
     text = open(os.path.join(HOST, "gpuLS.hpp")).read()
