@@ -1,7 +1,8 @@
 // lsmrc_kernels.cuh -- fused uplink-receiver kernels for sm_100a.
 //
-// One kernel template, two modes, replaces the reference's whole per-symbol
-// chain of library calls and tiny kernels (gpuLS.cu):
+// One kernel template replaces the reference's whole per-symbol chain of library
+// calls and tiny kernels (gpuLS.cu).  Two fused modes do the work
+// (a third, MODE_FFT, is the stand-alone batched transform behind gpuLS::batchedFFT):
 //
 //   MODE_PILOT : CP strip -> N-pt FFT -> drop DC -> LS divide by the pilot ->
 //                conj -> store Hconj[a][k] and sum_a |H|^2
@@ -28,7 +29,13 @@
 //   the register file (no shared or global intermediate, unlike
 //   gpuLS.cu:212-259 which writes and re-reads the full [S][A][K] tensor).
 //
-// N = 1024 uses P = 32, R2 = 32: one warp per row, one __syncwarp per row.
+// N = 1024 uses P = 32, R2 = 32: one warp per row, warp-level syncs only.
+//
+// Data kernel structure (details at the code): persistent CTAs pulling work items
+// from a global ticket counter; per item each team loops over the antennas with the
+// MRC accumulators in registers; for N = 1024 the teams of a CTA share every Hconj
+// row through a shared-memory ring filled by bulk async copies (TMA) on mbarriers;
+// inter-stage twiddles are fetched a chunk ahead of their use.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -93,11 +100,9 @@ struct KernelParams {
 
 template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false>
 struct Plan {
-    // REG_PF: data kernel loads row a+1 into registers while row a is still being processed:
-    // 1 = all loads right after stage 1, 2 = one load per MRC accumulation (as registers free up),
-    // 3 = the even-indexed half during the second half of the MRC, the odd half at the top of the
-    //     next row: the first four DIT layers of the even half need no odd sample, so they run
-    //     while the odd loads are still in flight
+    // REG_PF: data kernel loads row a+1 into registers while row a is still being processed
+    // (0 = off; 1 = all loads right after stage 1; 2 = one load per MRC accumulation, as the
+    // register pairs free up).  Only pays with a 255-register budget; off in the shipped plans.
     static constexpr int REG_PF = REG_PF_;
     // X_L1: prefetch the antenna-samples into L1 (and load them with L1 allocation) instead of L2
     static constexpr bool X_L1 = X_L1_;
@@ -114,7 +119,6 @@ struct Plan {
     static constexpr int PF_X = PF_X_, PF_H = PF_H_;
     static constexpr int N = N_, P = P_, R2 = R2_, R3 = R3_, TEAMS = TEAMS_, NBUF = NBUF_;
     static constexpr int T = N / P;        // threads per team == M1 (points per row of the tile)
-    static constexpr bool T_OK = (N_ / P_) <= 32 || true;
     static constexpr int ROW = T + 1;      // padded tile row (complex elements)
     static constexpr int NB2 = P / R2;     // stage-2 butterflies per thread
     static constexpr int NB3 = P / R3;     // stage-3 butterflies per thread (R3 > 1)
@@ -126,14 +130,14 @@ struct Plan {
     static constexpr int TWN = TW1 + TW2;
     static constexpr int TILE = P * ROW;   // complex elements per tile
     static constexpr size_t SMEM_BYTES = sizeof(float2) * (size_t)(TWN + HRING + TEAMS * NBUF * TILE);
-    static_assert(!H_RING_ || (TWN % 2 == 0 && T_OK), "ring rows must stay 16-byte aligned");
+    static_assert(!H_RING_ || TWN % 2 == 0, "ring rows must stay 16-byte aligned");
     static_assert(P * R2 * R3 == N, "plan must factor N");
     static_assert(P >= R2 && P >= R3, "thread must own whole butterflies");
     static_assert(THREADS <= 1024, "block too large");
     static_assert(T <= 32 || TEAMS <= 15, "named barriers 1..15");
 };
 
-__device__ __forceinline__ uint32_t smem_u32_c(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // streaming 64-bit load of one antenna-sample: read once, keep it out of L1
 __device__ __forceinline__ float2 ld_stream(const float2* p)
@@ -147,7 +151,7 @@ __device__ __forceinline__ float2 ld_stream(const float2* p)
 __device__ __forceinline__ float2 lds_volatile(const float2* p)
 {
     float2 r;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(smem_u32_c(p)));
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(smem_u32(p)));
     return r;
 }
 
@@ -169,7 +173,6 @@ __device__ __forceinline__ void prefetch_row(const float2* base, int n_elems, in
 }
 
 // ---- mbarrier + bulk async copy (TMA, 1-D) primitives ---------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -251,12 +254,7 @@ __device__ __forceinline__ void row_load(float2 (&v)[PL::P], const float2* __res
 {
 #pragma unroll
     for (int n1 = 0; n1 < PL::P; ++n1) {
-#ifdef LSMRC_FAKE_X  // experiment only: no global traffic for x (results are garbage)
-        v[n1] = make_float2(__int_as_float(0x3f800000 + n1 + t), (float)n1);
-        asm volatile("" : "+f"(v[n1].x), "+f"(v[n1].y));
-#else
         v[n1] = PL::X_L1 ? __ldg(x + n1 * PL::T + t) : ld_stream(x + n1 * PL::T + t);
-#endif
     }
 }
 
@@ -573,11 +571,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         }
 
         float2 v[P];
-        if (PL::REG_PF == 1 || PL::REG_PF == 2) row_load<PL>(v, x0, t);
-        if constexpr (PL::REG_PF == 3) {
-#pragma unroll
-            for (int n1 = 0; n1 < P; n1 += 2) v[n1] = ld_stream(x0 + n1 * T + t);
-        }
+        if (PL::REG_PF != 0) row_load<PL>(v, x0, t);
         const int n_rounds = (p.n_ant + AS - 1) / AS;
         for (int rd = 0; rd < n_rounds; ++rd) {
             // antenna of this round; teams whose slice has run out redo the last antenna and drop the result
@@ -597,11 +591,6 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             }
             if (PL::REG_PF == 0) {
                 row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
-            }
-            if constexpr (PL::REG_PF == 3) {
-                const float2* xr = x0 + (long long)a * p.ant_stride;
-#pragma unroll
-                for (int n1 = 1; n1 < P; n1 += 2) v[n1] = ld_stream(xr + n1 * T + t);
             }
             if (PF_X > 0 && a + PF_X * AS < p.n_ant)
                 prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X * AS) * p.ant_stride, N, t);
@@ -625,17 +614,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                     // with the next row's sample so its latency hides behind the rest of the MRC
                                     if (x_next != nullptr) v[sl] = ld_stream(x_next + sl * T + t);
                                 }
-                                if constexpr (PL::REG_PF == 3) {
-                                    if (sl >= P / 2 && x_next != nullptr)
-                                        v[2 * (sl - P / 2)] = ld_stream(x_next + 2 * (sl - P / 2) * T + t);
-                                }
                             } else {
-#ifdef LSMRC_FAKE_H  // experiment only
-                                float2 h = make_float2(1.f + sl, 0.5f);
-                                asm volatile("" : "+f"(h.x), "+f"(h.y));
-#else
                                 const float2 h = __ldg(h_src + bin);
-#endif
                                 if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
