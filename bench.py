@@ -313,6 +313,55 @@ def frontend_leg(m, dev_index, peak):
             "assemble_frac_of_hbm_peak": 2 * rx.numel() * 4 / (t_asm * 1e-3) / 1e9 / peak}
 
 
+def ring_stream_leg(m, n_frames=96):
+    """BASELINE config c3: 14-symbol slots of a 2048-pt / 128-antenna system streamed through the pinned
+    shared-memory ring (producer process = host/ring_feeder, consumer = host/stream_main: whole frames DMA'd
+    out of the ring on 3 rotating lanes, H2D of frame i+1 overlapping the kernels of frame i)."""
+    import shutil
+    import tempfile
+    import uuid
+
+    import numpy as np
+
+    cfg = m.CONFIGS["c3"]
+    host = os.path.join(ROOT, "gpu-accel-ofdm-ls-mrc_b200", "host")
+    if subprocess.run(["make", "-C", host, "--no-print-directory"], capture_output=True).returncode != 0:
+        return {"error": "host programs did not build"}
+    d = tempfile.mkdtemp(prefix="lsmrc_ring_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        base = 8  # distinct frames on disk; the feeder loops over them
+        rng = np.random.default_rng(3)
+        rx = rng.standard_normal((base, cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len, 2), dtype=np.float32)
+        rx.tofile(os.path.join(d, "rx.bin"))
+        m.synth.make_pilot(cfg.K, cfg.seed).tofile(os.path.join(d, "Pilots.dat"))
+        shm = "/lsmrc_" + uuid.uuid4().hex[:8]
+        ring = 4 * cfg.n_sym + 1
+        dims = ["--rows", str(cfg.n_ant), "--cols", str(cfg.fft_size), "--prefix", str(cfg.cp_len), "--syms", str(cfg.n_sym),
+                "--ring", str(ring), "--shm", shm]
+        feeder = subprocess.Popen([os.path.join(host, "bin", "ring_feeder"), "--file", os.path.join(d, "rx.bin"), "--frames", str(base),
+                                   "--repeat", str(n_frames // base)] + dims)
+        try:
+            r = subprocess.run([os.path.join(host, "bin", "stream_main"), "--qam", str(cfg.qam_bits), "--frames", str(n_frames),
+                                "--pilots", os.path.join(d, "Pilots.dat"), "--no-output"] + dims,
+                               cwd=d, capture_output=True, text=True, timeout=300)
+            feeder.wait(timeout=60)
+        finally:
+            if feeder.poll() is None:
+                feeder.kill()
+            if os.path.exists("/dev/shm" + shm):
+                os.unlink("/dev/shm" + shm)
+        if r.returncode != 0:
+            return {"error": (r.stdout + r.stderr)[-300:]}
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        out["workload"] = (f"c3: {cfg.fft_size}-pt FFT, {cfg.n_ant} antennas, {cfg.n_sym}-symbol slots, ring of {ring} slots "
+                           f"({cfg.rx_bytes_per_frame / 1e6:.1f} MB per frame), single producer process")
+        out["note"] = ("bounded by the single-threaded producer copying frames into the ring, then by PCIe; the consumer "
+                       "overlaps H2D, both kernels and D2H on 3 lanes")
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def workload_config(cfg, frames, e2e_frames):
     return {"workload": f"{cfg.name}: {cfg.fft_size}-pt FFT, CP {cfg.cp_len}, {cfg.n_ant} antennas, 1 pilot + "
                         f"{cfg.n_sym - 1} data symbols, {1 << cfg.qam_bits}-QAM",
@@ -462,13 +511,14 @@ def main():
         sustained = {"steps": n_long, "measured_over_last": len(dl), "data_kernel_ms": dms, "achieved": ach, "frac": ach / peak,
                      "value": F * cfg.antenna_samples_per_frame / ((dms + statistics.mean(pl)) * 1e-3), "clocks": ck2}
 
-    latency = others = frontend = None
+    latency = others = frontend = ring_stream = None
     if rank == 0 and world == 1 and not args.no_extras:
         del rx, rx_f, comb, bits
         torch.cuda.empty_cache()
         latency = latency_leg(m, local)
         others = other_configs_leg(m, local, peak)
         frontend = frontend_leg(m, local, peak)
+        ring_stream = ring_stream_leg(m)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -476,7 +526,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, F, Fe), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks, "plan": rcv.describe_plan(), "latency": latency,
-                "sustained": sustained, "other_configs": others, "frontend": frontend,
+                "sustained": sustained, "other_configs": others, "frontend": frontend, "ring_stream": ring_stream,
                 "parity": {"bit_errors_vs_source": bit_errors, "ber": ber, "frames_checked": 2}}
         print(json.dumps(line), flush=True)
     rcv.close()
