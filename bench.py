@@ -171,13 +171,23 @@ def cpu_baseline(cfg, n_threads, budget_s=12.0):
         oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
     dt = time.perf_counter() - t0
     frames = F0 * reps
-    return {"value": frames * cfg.antenna_samples_per_frame / dt, "unit": UNIT, "cores": n_threads, "kind": "port",
+    ref1 = None
+    if oracle_py.ref_binary(A, N, C, S) is not None:  # the reference's own build, as --impl reference times it
+        fr, secs = oracle_py.time_reference(make(2), pilot, C)
+        ref1 = {"value": fr * cfg.antenna_samples_per_frame / secs, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"{fr} frames through oracle/_ref (reference cpuLS.hpp + ring + file output), {secs:.2f} s"}
+    return {"reference_1core": ref1,
+            "value": frames * cfg.antenna_samples_per_frame / dt, "unit": UNIT, "cores": n_threads, "kind": "port",
             "sample": f"{frames} frames of {cfg.name} ({F0} frames x {reps} passes, {dt:.1f} s), oracle/cpuls_oracle.c "
                       f"-O3 -march=native, FFT = oracle/fft_shim.c (FFTW3 absent), frames split over {n_threads} threads"}
 
 
 def run_reference(args, cfg):
-    """--impl reference: the reference's CPU path (oracle port, all host threads), same metric/config"""
+    """--impl reference: the reference's own CPU implementation of the path, same metric and config.
+    When oracle/_ref holds a build of the reference's cpuLS.hpp for these dimensions (compiled from
+    /root/reference by oracle/Makefile; FFT through the shim because FFTW3 is absent) that binary is timed:
+    one process, one thread -- the reference is single-threaded and its ring name is hard-coded.  Otherwise
+    the oracle port runs with all host threads."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
@@ -185,28 +195,44 @@ def run_reference(args, cfg):
     from oracle import oracle_py
     import ofdm_b200 as m
 
-    oracle_py.build(ref=False)
-    n_threads = os.cpu_count() or 1
     A, N, C, S = cfg.n_ant, cfg.fft_size, cfg.cp_len, cfg.n_sym
     pilot = m.synth.make_pilot(cfg.K, cfg.seed)
     rng = np.random.default_rng(11)
-    # one step = a bounded sample: one frame per host thread (whole run stays within minutes)
-    F = max(1, min(n_threads, max(1, int(2e9 // cfg.rx_bytes_per_frame))))
-    rx = rng.standard_normal((F, S, A, N + C, 2), dtype=np.float32).view(np.complex64)[..., 0]
-    for _ in range(args.warmup):
-        oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=n_threads, fast=True)
-    dt = time.perf_counter() - t0
+
+    def frames(F):
+        return rng.standard_normal((F, S, A, N + C, 2), dtype=np.float32).view(np.complex64)[..., 0]
+
+    if oracle_py.ref_binary(A, N, C, S) is not None:
+        kind, cores = "reference", 1
+        _, t1 = oracle_py.time_reference(frames(1), pilot, C)        # calibration, also warms the page cache
+        F = int(max(1, min(4, 100.0 / max(args.steps + args.warmup, 1) / max(t1, 1e-3))))
+        rx = frames(F)
+        for _ in range(args.warmup):
+            oracle_py.time_reference(rx, pilot, C)
+        dt = 0.0
+        for _ in range(args.steps):
+            dt += oracle_py.time_reference(rx, pilot, C)[1]
+        sample = (f"{F} frames of {cfg.name} per step through oracle/_ref/cpuls_ref_{oracle_py.ref_case_name(A, N, C, S)}: the "
+                  f"reference's cpuLS.hpp + ring + Output_cpu.dat path, 1 thread, FFT = oracle/fft_shim.c (FFTW3 absent)")
+    else:
+        oracle_py.build(ref=False)
+        kind, cores = "port", os.cpu_count() or 1
+        F = max(1, min(cores, max(1, int(2e9 // cfg.rx_bytes_per_frame))))
+        rx = frames(F)
+        for _ in range(args.warmup):
+            oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=cores, fast=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle_py.demod_frames(rx, pilot, cfg.qam_bits, C, n_threads=cores, fast=True)
+        dt = time.perf_counter() - t0
+        sample = (f"{F} frames of {cfg.name} per step on {cores} host threads; oracle port of cpuLS.hpp "
+                  f"(no reference build for these dimensions in oracle/_ref)")
     value = args.steps * F * cfg.antenna_samples_per_frame / dt
-    sample = (f"{F} frames of {cfg.name} per step on {n_threads} host threads; oracle port of cpuLS.hpp "
-              f"(reference needs compile-time dims and FFTW3, see DESIGN.md)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, F, None),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

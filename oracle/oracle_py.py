@@ -176,3 +176,29 @@ def sync_to_slots(copy_buff: np.ndarray, S: int, N: int, cp: int, keep_cp: bool)
     out = np.empty((S, A, N + (cp if keep_cp else 0)), np.complex64)
     _lib().oracle_sync_to_slots(copy_buff.ctypes.data, A, per, S, N, cp, int(keep_cp), out.ctypes.data)
     return out
+
+
+def time_reference(rx: np.ndarray, pilot_asc, cp: int):
+    """Run the reference build on rx and return (frames, seconds of its frame loop) or None if no binary
+    exists for these dimensions.  Single process, single thread: that is what the reference is."""
+    import json
+
+    rx = np.ascontiguousarray(rx, dtype=np.complex64)
+    F, S, A, NC = rx.shape
+    exe = ref_binary(A, NC - cp, cp, S)
+    if exe is None:
+        return None
+    d = tempfile.mkdtemp(prefix="cpuls_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        rx.tofile(os.path.join(d, "rx.bin"))
+        args = [exe, d, os.path.join(d, "rx.bin"), str(F), os.path.join(d, "out")]
+        if pilot_asc is not None:
+            np.ascontiguousarray(pilot_asc, dtype=np.complex64).tofile(os.path.join(d, "pil.bin"))
+            args.append(os.path.join(d, "pil.bin"))
+        r = subprocess.run(args, check=True, timeout=600, capture_output=True, text=True)
+        t = json.loads(r.stdout.strip().splitlines()[-1])
+        return int(t["frames"]), float(t["seconds"])
+    finally:
+        import shutil
+
+        shutil.rmtree(d, ignore_errors=True)
