@@ -139,6 +139,25 @@ class ShMemSymBuff {
         std::memcpy(slot(w), Yf, slotBytes());
         store(kWrite, nxt);
     }
+    // Two-step form of writeNextSymbolWithWait for producers that fill the slot themselves (e.g. with
+    // several threads, or straight from a DMA engine): wait for a free slot, fill it, publish it.
+    complexF* acquireWriteSlot()
+    {
+        int w = load(kWrite);
+        if (w < 0) w = 0;
+        const int nxt = next(w);
+        while (nxt == load(kRead)) {
+            if (load(kSize) == -1) return nullptr;
+            relax();
+        }
+        return slot(w);
+    }
+    void commitWriteSlot()
+    {
+        int w = load(kWrite);
+        if (w < 0) w = 0;
+        store(kWrite, next(w));
+    }
     // Never blocks; overruns the reader if it is slow (ShMemSymBuff.hpp:464-482) -- the
     // behaviour rx_and_corr.cpp:83 relies on.
     template <typename T>

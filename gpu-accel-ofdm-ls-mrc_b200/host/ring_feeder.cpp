@@ -5,21 +5,82 @@
 // Creates the segment (master), waits for a consumer, streams the frames of a file.
 //
 //   ring_feeder --file rx.bin --rows A --cols N --prefix C --syms S --ring L [--frames F]
-//               [--shm /blah] [--repeat R] [--nowait]
+//               [--shm /blah] [--repeat R] [--nowait] [--threads T]
+// --threads T > 1 copies every symbol into its slot with T helper threads (a radio front end delivers
+// the antennas in parallel; one memcpy thread tops out near 9 GB/s and would hide what the consumer can do).
 // rx.bin holds [F][S][A][N+C] complex64.  --nowait uses writeNextSymbolNoWait like the
 // reference producer (can overrun a slow reader); the default blocks on a full ring.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ShMemSymBuff.hpp"
 
+// Splits one symbol copy over a few persistent helper threads (spin-synchronised: copies are ~100 us apart).
+class ParallelCopy {
+   public:
+    explicit ParallelCopy(int n) : n_(n > 1 ? n : 1)
+    {
+        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~ParallelCopy()
+    {
+        stop_.store(true, std::memory_order_release);
+        gen_.fetch_add(1, std::memory_order_release);
+        for (auto& t : workers_) t.join();
+    }
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        if (n_ == 1) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        dst_ = static_cast<char*>(dst);
+        src_ = static_cast<const char*>(src);
+        bytes_ = bytes;
+        done_.store(0, std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_release);
+        part(0);
+        while (done_.load(std::memory_order_acquire) != n_ - 1) sched_yield();
+    }
+
+   private:
+    void part(int i)
+    {
+        const size_t chunk = ((bytes_ + n_ - 1) / n_ + 63) & ~(size_t)63;
+        const size_t b = chunk * (size_t)i, e = b + chunk < bytes_ ? b + chunk : bytes_;
+        if (b < e) std::memcpy(dst_ + b, src_ + b, e - b);
+    }
+    void loop(int i)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            unsigned g;
+            while ((g = gen_.load(std::memory_order_acquire)) == seen) sched_yield();
+            seen = g;
+            if (stop_.load(std::memory_order_acquire)) return;
+            part(i);
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> done_{0};
+    std::atomic<bool> stop_{false};
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0;
+};
+
 int main(int argc, char** argv)
 {
-    int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, ring = 0, frames = -1, repeat = 1;
+    int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, ring = 0, frames = -1, repeat = 1, threads = 1;
     bool nowait = false;
     std::string shm = shmemID, file;
     for (int i = 1; i < argc; ++i) {
@@ -35,6 +96,7 @@ int main(int argc, char** argv)
         else if ((v = val("--ring"))) ring = atoi(v);
         else if ((v = val("--frames"))) frames = atoi(v);
         else if ((v = val("--repeat"))) repeat = atoi(v);
+        else if ((v = val("--threads"))) threads = atoi(v);
         else if ((v = val("--shm"))) shm = v;
         else if ((v = val("--file"))) file = v;
         else if (std::strcmp(argv[i], "--nowait") == 0) nowait = true;
@@ -59,12 +121,22 @@ int main(int argc, char** argv)
     in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(buf.size() * sizeof(complexF)));
 
     ShMemSymBuff ringbuf(shm, /*isMaster=*/1, rows, cols, cp, ring);
+    ParallelCopy pc(threads);
     for (int r = 0; r < repeat; ++r)
         for (int f = 0; f < frames; ++f)
             for (int s = 0; s < syms; ++s) {
                 complexF* sym = buf.data() + ((size_t)f * syms + (size_t)s) * slot;
-                if (nowait) ringbuf.writeNextSymbolNoWait(sym);
-                else ringbuf.writeNextSymbolWithWait(sym);
+                if (threads > 1) {
+                    // same protocol as writeNextSymbolWithWait, with the slot filled by the helper threads
+                    complexF* dst = ringbuf.acquireWriteSlot();
+                    if (!dst) break;  // reader gone
+                    pc.copy(dst, sym, ringbuf.slotBytes());
+                    ringbuf.commitWriteSlot();
+                } else if (nowait) {
+                    ringbuf.writeNextSymbolNoWait(sym);
+                } else {
+                    ringbuf.writeNextSymbolWithWait(sym);
+                }
             }
     // keep the segment alive until the reader has drained it and gone away
     while (ringbuf.available() > 0 && !ringbuf.readerGone()) sched_yield();
