@@ -30,6 +30,7 @@ ABI = {
     "lsmrc_set_pilot": (c_int, [c_void_p, c_void_p, c_int]),
     "lsmrc_set_pilot_file": (c_int, [c_void_p, c_char_p]),
     "lsmrc_demod_frames_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsmrc_demod_frames_device_soft": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float]),
     "lsmrc_demod_frames_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsmrc_first_vector": (c_int, [c_void_p, c_void_p, c_int]),
     "lsmrc_demod_one_symbol": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
@@ -175,6 +176,10 @@ class LsMrcReceiver:
     def demod_frames_device(self, d_rx, n_frames, d_combined, d_bits=None, d_hconj=None, d_hsqrd=None):
         self._ck(self.lib.lsmrc_demod_frames_device(self.h, _ptr(d_rx), n_frames, _ptr(d_hconj), _ptr(d_hsqrd),
                                                     _ptr(d_combined), _ptr(d_bits)))
+
+    def demod_frames_device_soft(self, d_rx, n_frames, d_combined, d_llr, noise_var, d_bits=None):
+        self._ck(self.lib.lsmrc_demod_frames_device_soft(self.h, _ptr(d_rx), n_frames, _ptr(d_combined), _ptr(d_bits),
+                                                         _ptr(d_llr), noise_var))
 
     def demod_frames_host(self, h_rx, n_frames, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
         self._ck(self.lib.lsmrc_demod_frames_host(self.h, _ptr(h_rx), n_frames, _ptr(h_hconj), _ptr(h_hsqrd),

@@ -287,6 +287,8 @@ struct lsmrc_ctx {
     bool have_channel = false;
     std::vector<Lane> lanes;
     unsigned long long* d_hit = nullptr;  // frame-sync first-hit key
+    float* soft_llr = nullptr;            // set for the duration of a *_soft call
+    float soft_inv_noise = 1.f;
     bool timing = false;
     static constexpr int kEvRing = 256;          // timed calls remembered for lsmrc_kernel_ms_history
     cudaEvent_t ev[kEvRing][3] = {};             // [call % kEvRing] -> {start, after pilot, after data}
@@ -334,6 +336,8 @@ KernelParams base_params(lsmrc_ctx* h)
     p.pilot_bin = h->d_pilot_bin;
     p.bits_row_bytes = (int)h->row_bytes;
     p.twiddles = h->d_tw;
+    p.llr = h->soft_llr;
+    p.inv_noise_var = h->soft_inv_noise;
     return p;
 }
 
@@ -754,6 +758,27 @@ int lsmrc_demod_frames_device(lsmrc_handle h, const void* d_rx, int n_frames, vo
     return launch_frames(h, compute_stream(h), static_cast<const float2*>(d_rx), n_frames, h->dev_ch,
                          static_cast<float2*>(d_hconj), static_cast<float*>(d_hsqrd), static_cast<float2*>(d_combined),
                          static_cast<uint8_t*>(d_bits), h->timing);
+}
+
+int lsmrc_demod_frames_device_soft(lsmrc_handle h, const void* d_rx, int n_frames, void* d_combined, void* d_bits,
+                                   void* d_llr, float noise_var)
+{
+    if (!h || !d_rx || !d_combined || !d_llr) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (!(noise_var > 0.f)) return fail(h, LSMRC_ERR_INVALID, "noise_var must be positive");
+    if (n_frames < 0) return fail(h, LSMRC_ERR_INVALID, "n_frames < 0");
+    if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
+    if (n_frames == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    {
+        const int rc = ensure_chan(h, h->dev_ch, n_frames, compute_stream(h));
+        if (rc != LSMRC_OK) return rc;
+    }
+    h->soft_llr = static_cast<float*>(d_llr);
+    h->soft_inv_noise = 1.0f / noise_var;
+    const int rc = launch_frames(h, compute_stream(h), static_cast<const float2*>(d_rx), n_frames, h->dev_ch, nullptr, nullptr,
+                                 static_cast<float2*>(d_combined), static_cast<uint8_t*>(d_bits), h->timing);
+    h->soft_llr = nullptr;
+    return rc;
 }
 
 int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,

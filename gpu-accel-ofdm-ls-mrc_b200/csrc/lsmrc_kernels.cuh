@@ -95,6 +95,10 @@ struct KernelParams {
     float2* combined;  // [F][n_sym_work][K], ascending frequency
     uint8_t* bits;     // [F][n_sym_work][row_bytes] or nullptr
     int bits_row_bytes;
+    // optional soft output: max-log LLRs [F][n_sym_work][K][qam_bits] (ascending frequency, bit order as
+    // in the packed bits; LLR > 0 <=> bit 0), scaled by sum|H|^2 / noise_var
+    float* llr;
+    float inv_noise_var;
     const float2* twiddles;  // plan table: tw1 [(P-1)][T] then tw2 [(R2-1)][R3]
 };
 
@@ -255,6 +259,30 @@ __device__ __forceinline__ void row_load(float2 (&v)[PL::P], const float2* __res
 #pragma unroll
     for (int n1 = 0; n1 < PL::P; ++n1) {
         v[n1] = PL::X_L1 ? __ldg(x + n1 * PL::T + t) : ld_stream(x + n1 * PL::T + t);
+    }
+}
+
+// Max-log LLRs of the Gray-mapped square QAM of demap_symbol(), the usual piecewise-linear form:
+//   bit 0/1 (sign bits):       4a*rho * re|im
+//   16-QAM bit 2/3:            4a*rho * (2a - |re|im|)
+//   64-QAM bit 2/3, bit 4/5:   4a*rho * (4a - |.|),  4a*rho * (2a - ||.| - 4a|)
+// a = 1/sqrt(2), 1/sqrt(10), 1/sqrt(42); rho = sum|H|^2 / noise_var is the post-MRC SNR scale.
+// Same constants and operation order as oracle/cpuls_oracle.c soft_one().
+template <int B>
+__device__ __forceinline__ void soft_symbol(float re, float im, float rho, float* out)
+{
+    constexpr float a = (B == 2) ? (float)0.7071067811865476 : (B == 4) ? (float)0.31622776601683794 : (float)0.1543033499620919;
+    const float g = __fmul_rn(4.0f * a, rho);
+    out[0] = __fmul_rn(g, re);
+    out[1] = __fmul_rn(g, im);
+    if (B == 4) {
+        out[2] = __fmul_rn(g, __fsub_rn(2.0f * a, fabsf(re)));
+        out[3] = __fmul_rn(g, __fsub_rn(2.0f * a, fabsf(im)));
+    } else if (B == 6) {
+        out[2] = __fmul_rn(g, __fsub_rn(4.0f * a, fabsf(re)));
+        out[3] = __fmul_rn(g, __fsub_rn(4.0f * a, fabsf(im)));
+        out[4] = __fmul_rn(g, __fsub_rn(2.0f * a, fabsf(__fsub_rn(fabsf(re), 4.0f * a))));
+        out[5] = __fmul_rn(g, __fsub_rn(2.0f * a, fabsf(__fsub_rn(fabsf(im), 4.0f * a))));
     }
 }
 
@@ -649,6 +677,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         float2* out_row = p.combined + ((long long)f * p.n_sym_work + s) * K;
         uint8_t* s_idx = reinterpret_cast<uint8_t*>(my_tiles);
         uint8_t* bits_row = p.bits ? p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes : nullptr;
+        float* llr_row = p.llr ? p.llr + ((long long)f * p.n_sym_work + s) * K * p.qam_bits : nullptr;
         auto finish = [&](auto bconst) {
             constexpr int b = decltype(bconst)::value;
             float einv[P];
@@ -671,6 +700,12 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                     const int pos = (bin < N / 2) ? (bin - 1 + N / 2) : (bin - N / 2);
                     if (valid) out_row[pos] = o;
                     s_idx[pos] = (uint8_t)demap_symbol(o.x, o.y, b);
+                    if (llr_row != nullptr && valid) {
+                        float l[b];
+                        soft_symbol<b>(o.x, o.y, __fmul_rn(einv[sl], p.inv_noise_var), l);
+#pragma unroll
+                        for (int q = 0; q < b; ++q) llr_row[pos * b + q] = l[q];
+                    }
                 }
             }
             if (bits_row != nullptr) {

@@ -69,7 +69,7 @@ class gpuLS {
     // Runtime dimensions.  ring_slots == 0 -> no ring (device / host tensors only).
     gpuLS(int rows, int cols, int cp, int n_sym, int qam_bits, int ring_slots, const std::string& shm_uid,
           int is_master, int device)
-        : rows_(rows), cols_(cols), cp_(cp), n_sym_(n_sym)
+        : rows_(rows), cols_(cols), cp_(cp), n_sym_(n_sym), qam_bits_(qam_bits)
     {
         lsmrc_config c;
         c.n_ant = rows;
@@ -260,10 +260,23 @@ class gpuLS {
         demodOneFrameCUDA(dY, Y, dX, Hconj, Hsqrd, rows, cols);
     }
 
+    // Soft output (no reference counterpart): as demodOneFrameCUDA plus max-log LLRs, llr (host) is
+    // [S-1][cols-1][qamBits()] floats in ascending-frequency order, LLR > 0 <=> bit 0.
+    void demodOneFrameSoftCUDA(cuFloatComplex* dY, float* llr, cuFloatComplex* Y, float noiseVar, int rows, int cols)
+    {
+        checkDims(rows, cols);
+        const size_t n_out = (size_t)(n_sym_ - 1) * (size_t)(cols - 1);
+        if (!d_comb_) check(lsmrc_dev_alloc(handle, n_out * sizeof(cuFloatComplex), &d_comb_), "lsmrc_dev_alloc");
+        if (!d_llr_) check(lsmrc_dev_alloc(handle, n_out * qam_bits_ * sizeof(float), &d_llr_), "lsmrc_dev_alloc");
+        check(lsmrc_demod_frames_device_soft(handle, Y, 1, d_comb_, nullptr, d_llr_, noiseVar), "lsmrc_demod_frames_device_soft");
+        check(lsmrc_copy_to_host(handle, dY, d_comb_, n_out * sizeof(cuFloatComplex)), "lsmrc_copy_to_host");
+        check(lsmrc_copy_to_host(handle, llr, d_llr_, n_out * qam_bits_ * sizeof(float)), "lsmrc_copy_to_host");
+    }
+
     // demapped bits of the most recent demodOneSymbol (one row) / demodOneFrame (S-1 rows)
     const uint8_t* lastBits() const { return bits_.data(); }
     size_t bitsRowBytes() const { return lsmrc_bits_row_bytes(cols_, qamBits()); }
-    int qamBits() const { return (int)((bits_.size() * 8) / ((size_t)(n_sym_ > 1 ? n_sym_ - 1 : 1) * (size_t)(cols_ - 1))); }
+    int qamBits() const { return qam_bits_; }
 
    private:
     void check(int rc, const char* what)
@@ -311,9 +324,10 @@ class gpuLS {
         }
         return d_scratch_;
     }
-    int rows_, cols_, cp_, n_sym_;
+    int rows_, cols_, cp_, n_sym_, qam_bits_;
     std::vector<uint8_t> bits_;
     void* d_comb_ = nullptr;
+    void* d_llr_ = nullptr;
     void* d_scratch_ = nullptr;
     size_t scratch_bytes_ = 0;
 };

@@ -94,6 +94,13 @@ int lsmrc_set_pilot_file(lsmrc_handle h, const char *path);
 int lsmrc_demod_frames_device(lsmrc_handle h, const void *d_rx, int n_frames, void *d_hconj,
                               void *d_hsqrd, void *d_combined, void *d_bits);
 
+/* Same as lsmrc_demod_frames_device plus soft output (SURVEY 8f, rank 2 -- not in the reference):
+ * d_llr [F][S-1][K][b] float, ascending frequency, bit order as in the packed bits, LLR > 0 <=> bit 0.
+ * Max-log piecewise-linear LLRs scaled by the post-MRC SNR sum|H|^2 / noise_var (noise_var: noise variance
+ * per antenna and subcarrier after the FFT, supplied by the caller).  d_bits may be NULL. */
+int lsmrc_demod_frames_device_soft(lsmrc_handle h, const void *d_rx, int n_frames, void *d_combined,
+                                   void *d_bits, void *d_llr, float noise_var);
+
 /* ---- whole frames, host buffers (replaces gpuLS::demodOneFrame gpuLS.cu:475: H2D,
  *      compute, D2H inside).  Frames are cut into chunks of <= max_frames and pipelined
  *      over n_lanes streams so that H2D(i+1), kernels(i) and D2H(i-1) overlap.  Host

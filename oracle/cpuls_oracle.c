@@ -173,7 +173,7 @@ void oracle_one_symbol(const oc_complex *rx_sym, const oc_complex *hconj, const 
 /* Hard decision, Gray-mapped square QAM of 3GPP TS 38.211 5.1.3-5.1.5, unit
  * average power.  Strict comparisons: +-0.0 -> bit 0.  Bits are packed LSB
  * first; symbol i occupies stream bits [i*b, i*b+b).  The same fp32 constants
- * appear in the CUDA kernel (csrc/lsmrc_demap.cuh). */
+ * appear in the CUDA kernel (csrc/lsmrc_kernels.cuh demap_symbol). */
 #define QAM16_T ((float)0.6324555320336759)   /* 2/sqrt(10) */
 #define QAM64_T4 ((float)0.6172133998483676)  /* 4/sqrt(42) */
 #define QAM64_T2 ((float)0.3086066999241838)  /* 2/sqrt(42) */
@@ -210,6 +210,36 @@ void oracle_demap_row(const oc_complex *sym, int K, int qam_bits, uint8_t *packe
                 if (v & (1u << q)) packed[pos >> 3] |= (uint8_t)(1u << (pos & 7u));
             }
         }
+    }
+}
+
+/* Max-log LLRs (not in the reference).  Piecewise-linear form for the mapping above;
+ * LLR > 0 <=> bit 0; rho = sum|H|^2 / noise_var.  Same constants and order as soft_symbol() in the kernel. */
+static void soft_one(float re, float im, float rho, int qam_bits, float *out)
+{
+    const float a = qam_bits == 2 ? (float)0.7071067811865476 : qam_bits == 4 ? (float)0.31622776601683794 : (float)0.1543033499620919;
+    const float g = (4.0f * a) * rho;
+    out[0] = g * re;
+    out[1] = g * im;
+    if (qam_bits == 4) {
+        out[2] = g * (2.0f * a - fabsf(re));
+        out[3] = g * (2.0f * a - fabsf(im));
+    } else if (qam_bits == 6) {
+        out[2] = g * (4.0f * a - fabsf(re));
+        out[3] = g * (4.0f * a - fabsf(im));
+        out[4] = g * (2.0f * a - fabsf(fabsf(re) - 4.0f * a));
+        out[5] = g * (2.0f * a - fabsf(fabsf(im) - 4.0f * a));
+    }
+}
+
+/* sym [K] combined symbols (ascending frequency), hsqrd_bin [K] in FFT-bin order, llr [K][b] */
+void oracle_soft_demap_row(const oc_complex *sym, const float *hsqrd_bin, int K, int qam_bits, float noise_var, float *llr)
+{
+    int i;
+    const float inv = 1.0f / noise_var;
+    for (i = 0; i < K; i++) {
+        const int bin_idx = (i + (K - 1) / 2) % K; /* inverse of shiftOneRow: sorted[i] = out[(i+(K-1)/2) mod K] */
+        soft_one(sym[i].real, sym[i].imag, hsqrd_bin[bin_idx] * inv, qam_bits, llr + (size_t)i * qam_bits);
     }
 }
 

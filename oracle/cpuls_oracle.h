@@ -46,6 +46,9 @@ void oracle_one_symbol(const oc_complex *rx_sym, const oc_complex *hconj, const 
 /* hard demap (not in the reference; definition in DESIGN.md / SURVEY.md 8c) */
 void oracle_demap_row(const oc_complex *sym, int K, int qam_bits, uint8_t *packed, uint8_t *idx);
 
+/* max-log LLRs of one combined row (new; definition in DESIGN.md): llr [K][b], LLR > 0 <=> bit 0 */
+void oracle_soft_demap_row(const oc_complex *sym, const float *hsqrd_bin, int K, int qam_bits, float noise_var, float *llr);
+
 /* whole batch: rx [F][S][A][N+C]; hconj [F][A][K]; hsqrd [F][K]; combined
  * [F][S-1][K]; bits [F][S-1][row_bytes].  n_threads >= 1 splits frames. */
 int oracle_demod_frames(const oc_complex *rx, const oc_complex *pilot_asc, int F, int S, int A,

@@ -49,6 +49,9 @@ def _lib(fast: bool = False) -> ctypes.CDLL:
         lib.oracle_demap_row.restype = None
         lib.oracle_demap_row.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_soft_demap_row.restype = None
+        lib.oracle_soft_demap_row.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                              ctypes.c_void_p]
         lib.oracle_sync_correlate.restype = ctypes.c_int
         lib.oracle_sync_correlate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -202,3 +205,16 @@ def time_reference(rx: np.ndarray, pilot_asc, cp: int):
         import shutil
 
         shutil.rmtree(d, ignore_errors=True)
+
+
+def soft_demap(combined: np.ndarray, hsqrd: np.ndarray, qam_bits: int, noise_var: float) -> np.ndarray:
+    """combined [F,S-1,K], hsqrd [F,K] -> max-log LLRs [F,S-1,K,b] (LLR > 0 <=> bit 0)"""
+    combined = np.ascontiguousarray(combined, np.complex64)
+    hsqrd = np.ascontiguousarray(hsqrd, np.float32)
+    F, D, K = combined.shape
+    out = np.empty((F, D, K, qam_bits), np.float32)
+    for f in range(F):
+        for s in range(D):
+            _lib().oracle_soft_demap_row(combined[f, s].ctypes.data, hsqrd[f].ctypes.data, K, qam_bits, noise_var,
+                                         out[f, s].ctypes.data)
+    return out

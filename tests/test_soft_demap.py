@@ -1,0 +1,62 @@
+"""Soft output (max-log LLRs; SURVEY 8f rank 2 -- new, the reference has no demapper at all): the oracle's
+definition is self-consistent with the hard demapper, and the CUDA epilogue reproduces it."""
+import numpy as np
+import pytest
+
+from util import assert_close
+
+
+@pytest.mark.parametrize("b", [2, 4, 6])
+def test_llr_sign_is_the_hard_decision_and_scales_with_snr(oracle, ofdm, b):
+    rng = np.random.default_rng(b)
+    K = 63
+    sym = (1.3 * (rng.standard_normal((1, 2, K)) + 1j * rng.standard_normal((1, 2, K))) / np.sqrt(2)).astype(np.complex64)
+    e = (1.0 + rng.random((1, K))).astype(np.float32)
+    llr = oracle.soft_demap(sym, e, b, noise_var=0.5)
+    idx = np.stack([oracle.demap_row(sym[0, s], b)[1] for s in range(2)])
+    hard = (idx[..., None] >> np.arange(b)) & 1
+    nz = np.abs(llr[0]) > 1e-6
+    assert np.array_equal((llr[0] < 0)[nz], hard.astype(bool)[nz])       # LLR < 0 <=> bit 1
+    assert np.allclose(oracle.soft_demap(sym, e, b, noise_var=0.25), 2 * llr, rtol=1e-6)   # 1/noise_var scaling
+    assert np.allclose(oracle.soft_demap(sym, 3 * e, b, noise_var=0.5), 3 * llr, rtol=1e-6)  # sum|H|^2 scaling
+
+
+def test_llr_known_values(oracle):
+    a = 1 / np.sqrt(10)
+    sym = np.array([[[3 * a - 1j * a, 0.5 * a + 2 * a * 1j, 0]]], np.complex64)   # K = 3
+    e = np.ones((1, 3), np.float32)
+    llr = oracle.soft_demap(sym, e, 4, noise_var=1.0)[0, 0]
+    want0 = 4 * a * np.array([3 * a, -a, 2 * a - 3 * a, 2 * a - a])
+    assert np.allclose(llr[0], want0, rtol=1e-6)
+    assert np.allclose(llr[2], 4 * a * np.array([0, 0, 2 * a, 2 * a]), rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(4, 64, 16, 6, 2, 3), (8, 1024, 64, 4, 4, 2), (6, 1024, 64, 3, 6, 2), (5, 2048, 144, 3, 4, 1)])
+def test_gpu_llrs_match_oracle(ofdm, oracle, dims):
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db={2: 10.0, 4: 15.0, 6: 20.0}[b], seed=17)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    noise_var = 0.37
+    want = oracle.soft_demap(ref["combined"], ref["hsqrd"], b, noise_var)
+    dev = torch.device("cuda:0")
+    rx = torch.view_as_real(torch.from_numpy(d["rx"]).to(dev)).contiguous()
+    comb = torch.empty((F, S - 1, K, 2), device=dev)
+    bits = torch.empty((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+    llr = torch.full((F, S - 1, K, b), float("nan"), device=dev)
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(d["pilot_asc"])
+        r.demod_frames_device_soft(rx, F, comb, llr, noise_var, bits)
+        r.sync()
+        with pytest.raises(ofdm.LsmrcError):
+            r.demod_frames_device_soft(rx, F, comb, llr, 0.0, bits)
+    got = llr.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert_close(got, want, "LLRs", tol=2e-5)
+    assert np.array_equal(bits.cpu().numpy(), ref["bits"])
+    hard = np.unpackbits(ref["bits"], axis=-1, bitorder="little")[..., : K * b].reshape(F, S - 1, K, b).astype(bool)
+    big = np.abs(want) > 1e-3 * np.abs(want).max()
+    assert np.array_equal((got < 0)[big], hard[big])
