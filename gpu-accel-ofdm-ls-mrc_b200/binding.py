@@ -62,6 +62,8 @@ ABI = {
     "lsmrc_set_stream": (c_int, [c_void_p, c_void_p]),
     "lsmrc_sync": (c_int, [c_void_p]),
     "lsmrc_set_timing": (c_int, [c_void_p, c_int]),
+    "lsmrc_set_oneshot": (c_int, [c_void_p, c_int]),
+    "lsmrc_oneshot_count": (ctypes.c_longlong, [c_void_p]),
     "lsmrc_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
     "lsmrc_kernel_ms_history": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_int)]),
     "lsmrc_launch_count": (c_longlong, [c_void_p]),
@@ -269,6 +271,14 @@ class LsMrcReceiver:
 
     def sync(self):
         self._ck(self.lib.lsmrc_sync(self.h))
+
+    def set_oneshot(self, mode=2):
+        """Launch policy for launch-latency-bound batches: 2 (default) one fused kernel, pinned host buffers
+        processed in place; 1 fused kernel with staged copies; 0 always pilot + data kernels."""
+        self._ck(self.lib.lsmrc_set_oneshot(self.h, int(mode)))
+
+    def oneshot_count(self) -> int:
+        return int(self.lib.lsmrc_oneshot_count(self.h))
 
     def set_timing(self, on=True):
         self._ck(self.lib.lsmrc_set_timing(self.h, int(on)))

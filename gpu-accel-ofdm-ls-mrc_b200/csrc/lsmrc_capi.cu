@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -32,6 +33,85 @@ struct PlanOps {
     cudaError_t (*prepare)(int* data_ctas_per_sm, int* pilot_ctas_per_sm);
     cudaError_t (*launch)(int mode, const KernelParams&, cudaStream_t, int max_data_ctas, unsigned* grid_out, long long* items_out);
 };
+
+// The one-launch kernel (MODE_ONESHOT) of a plan.  Small FFT sizes have a dedicated latency plan:
+// more threads per row than the throughput plan, so the serial instruction chain of one thread --
+// what a single small frame is bound by -- is several times shorter.
+struct OneshotOps {
+    int N, P, R2, R3, teams, threads, twn;
+    void (*fill_twiddles)(float2*);
+    cudaError_t (*prepare)(int smem_optin);
+    // antenna split to use for this batch, 0 when the mode does not apply
+    int (*split)(int n_frames, int n_sym_work, int n_ant, int n_sms, size_t smem_optin);
+    cudaError_t (*launch)(const KernelParams&, cudaStream_t);
+};
+
+template <class PL>
+void fill_twiddles_impl(float2* tw);
+
+#ifndef LSMRC_ONESHOT
+#define LSMRC_ONESHOT 1
+#endif
+constexpr int kOneshotMinb = 1;  // latency mode: one CTA per SM, the full register file
+
+template <class PL>
+size_t oneshot_smem(int n_ant)
+{
+    return PL::SMEM_BYTES + (size_t)n_ant * PL::N * sizeof(float2) + (size_t)PL::N * sizeof(float);
+}
+
+// The one-launch mode pays when the call is launch-latency bound: every CTA repeats the channel
+// estimate, so it is used only when that is at most two rounds of row FFTs, the whole batch fits
+// in less than one CTA per SM, and conj(H) of a frame fits in shared memory.
+template <class PL>
+int oneshot_split_impl(int n_frames, int n_sym_work, int n_ant, int n_sms, size_t smem_optin)
+{
+    if (!LSMRC_ONESHOT || n_sym_work < 1) return 0;
+    if (oneshot_smem<PL>(n_ant) > smem_optin) return 0;
+    if ((n_ant + PL::TEAMS - 1) / PL::TEAMS > 2) return 0;
+    int as = 1;
+    auto ctas = [&](int a) {
+        const int slots = PL::TEAMS / a;
+        return (long long)n_frames * ((n_sym_work + slots - 1) / slots);
+    };
+    if (ctas(1) > n_sms) return 0;
+    while (as * 2 <= PL::TEAMS && as * 2 <= n_ant && ctas(as * 2) <= n_sms) as *= 2;
+    return as;
+}
+
+template <class PL>
+cudaError_t oneshot_prepare_impl(int smem_optin)
+{
+    return cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_ONESHOT, kOneshotMinb>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+}
+
+template <class PL>
+cudaError_t oneshot_launch_impl(const KernelParams& p, cudaStream_t st)
+{
+    const int slots = PL::TEAMS / p.ant_split;
+    const unsigned grid = (unsigned)(p.n_frames * ((p.n_sym_work + slots - 1) / slots));
+    lsmrc_kernel<PL, MODE_ONESHOT, kOneshotMinb><<<grid, PL::THREADS, oneshot_smem<PL>(p.n_ant), st>>>(p);
+    return cudaGetLastError();
+}
+
+template <class PL>
+OneshotOps make_oneshot_ops()
+{
+    OneshotOps o;
+    o.N = PL::N;
+    o.P = PL::P;
+    o.R2 = PL::R2;
+    o.R3 = PL::R3;
+    o.teams = PL::TEAMS;
+    o.threads = PL::THREADS;
+    o.twn = PL::TWN;
+    o.fill_twiddles = &fill_twiddles_impl<PL>;
+    o.prepare = &oneshot_prepare_impl<PL>;
+    o.split = &oneshot_split_impl<PL>;
+    o.launch = &oneshot_launch_impl<PL>;
+    return o;
+}
+
 
 template <class PL>
 void fill_twiddles_impl(float2* tw)
@@ -226,6 +306,24 @@ const PlanOps* find_plan(int N)
     return nullptr;
 }
 
+// One-launch kernels.  64..256 points get a latency plan (8 points per thread instead of 16: a
+// thread's serial chain is what bounds a single small frame); larger sizes reuse the throughput plan.
+const OneshotOps* find_oneshot_plan(int N)
+{
+    static const OneshotOps plans[] = {
+        make_oneshot_ops<Plan<64, 8, 8, 1, 16, 2>>(),
+        make_oneshot_ops<Plan<128, 8, 4, 4, 16, 1>>(),
+        make_oneshot_ops<Plan<256, 8, 8, 4, 8, 1>>(),
+        make_oneshot_ops<Plan<512, 32, 16, 1, 8, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, 0>>(),
+        make_oneshot_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>>(),
+        make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>>(),
+        make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>>(),
+    };
+    for (const OneshotOps& o : plans)
+        if (o.N == N) return &o;
+    return nullptr;
+}
+
 // device-side channel state for a batch of frames (internal layouts, see KernelParams)
 struct ChanState {
     float2* hwork = nullptr;          // [frames][A][N]
@@ -250,6 +348,10 @@ struct Lane {
     float2* h_comb = nullptr;
     uint8_t* h_bits = nullptr;
     float2* h_hconj = nullptr;
+    // device-visible aliases of the three pinned buffers (in-place ring path)
+    float2* a_comb = nullptr;
+    uint8_t* a_bits = nullptr;
+    float2* a_hconj = nullptr;
     bool busy = false;
 };
 
@@ -265,8 +367,16 @@ struct lsmrc_ctx {
     size_t slot_elems = 0;   // A*(N+C)
     size_t frame_elems = 0;  // S*slot
     const PlanOps* ops = nullptr;
+    const OneshotOps* one_ops = nullptr;  // one-launch kernel (own plan, own twiddle table)
+    float2* d_one_tw = nullptr;
     int max_data_ctas = 1;  // persistent data-kernel grid: resident CTAs per SM x SM count
     int pilot_wave = 1;     // pilot-kernel CTAs resident at once on the whole GPU
+    int n_sms = 1;
+    size_t smem_optin = 0;
+    long long oneshot_calls = 0;  // batches served by the one-launch kernel
+    long long zero_copy_calls = 0;  // ... of which on pinned host buffers in place
+    bool oneshot = true;
+    bool zero_copy = true;        // one-launch kernel reads/writes pinned host buffers in place (small frames)
     float2* d_tw = nullptr;
     float2* d_pilot_bin = nullptr;
     bool have_pilot = false;
@@ -328,6 +438,9 @@ KernelParams base_params(lsmrc_ctx* h)
     std::memset(&p, 0, sizeof(p));
     const lsmrc_config& c = h->cfg;
     p.sym_stride = (long long)h->slot_elems;
+    p.rx2 = nullptr;
+    p.split_sym = 0x7fffffff;
+    p.rx_align4 = 0;
     p.frame_stride = (long long)h->frame_elems;
     p.ant_stride = c.fft_size + c.cp_len;
     p.cp = c.cp_len;
@@ -426,17 +539,57 @@ int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, fl
     return LSMRC_OK;
 }
 
-// pilot + data launches for n_frames whole frames (ch must hold >= n_frames)
+// where the symbols of ONE frame sit when they are not a dense [S][A][N+C] block (ring slots read in place)
+struct RxLayout {
+    long long sym_stride;  // complex elements between consecutive symbols
+    const float2* rx2;     // symbols >= split_sym continue here (ring wrap); nullptr = contiguous
+    int split_sym;
+    int align4;            // slots are 4- but not 8-byte aligned (the reference ring's 12-byte header)
+};
+
+// pilot + data launches for n_frames whole frames (ch must hold >= n_frames); `lay` only with the
+// one-launch kernel (the caller has checked that it applies)
 int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frames, ChanState& ch, float2* d_hconj,
-                  float* d_hsqrd, float2* d_comb, uint8_t* d_bits, bool timed)
+                  float* d_hsqrd, float2* d_comb, uint8_t* d_bits, bool timed, const RxLayout* lay = nullptr)
 {
     KernelParams p = base_params(h);
     p.rx = d_rx;
+    if (lay) {
+        p.sym_stride = lay->sym_stride;
+        p.rx_align4 = lay->align4;
+        if (lay->rx2) {
+            p.rx2 = lay->rx2;
+            p.split_sym = lay->split_sym;
+        }
+    }
     p.n_frames = n_frames;
     p.combined = d_comb;
     p.bits = d_bits;
     cudaEvent_t* ev = h->ev[h->ev_calls % lsmrc_ctx::kEvRing];
     if (timed) CK(h, cudaEventRecord(ev[0], st));
+    const int one_as = (h->oneshot && h->one_ops && h->cfg.n_sym > 1)
+                           ? h->one_ops->split(n_frames, h->cfg.n_sym - 1, h->cfg.n_ant, h->n_sms, h->smem_optin)
+                           : 0;
+    if (one_as > 0) {
+        // launch-latency bound batch: channel estimate and data symbols in one kernel
+        p.first_sym = 1;
+        p.n_sym_work = h->cfg.n_sym - 1;
+        p.hwork = ch.hwork;
+        p.hconj = d_hconj;
+        p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
+        p.ant_split = one_as;
+        p.twiddles = h->d_one_tw;
+        if (timed) CK(h, cudaEventRecord(ev[1], st));
+        CK(h, h->one_ops->launch(p, st));
+        h->launches++;
+        h->oneshot_calls++;
+        if (timed) {
+            CK(h, cudaEventRecord(ev[2], st));
+            h->ev_calls++;
+        }
+        return LSMRC_OK;
+    }
+    if (lay) return fail(h, LSMRC_ERR_STATE, "in-place ring layout without the one-launch kernel");
     int rc = launch_pilot(h, st, p, ch, d_hconj, d_hsqrd);
     if (rc != LSMRC_OK) return rc;
     if (timed) CK(h, cudaEventRecord(ev[1], st));
@@ -449,6 +602,17 @@ int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frame
         h->ev_calls++;
     }
     return LSMRC_OK;
+}
+
+// device-visible alias of a pinned (page-locked, mapped) host buffer; nullptr for anything else
+void* mapped_alias(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 bool is_pinned_or_device(const void* p)
@@ -663,6 +827,8 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
         if (per_sm < 1 || pilot_per_sm < 1) { h->err = "kernel does not fit on an SM"; return bail(LSMRC_ERR_CUDA); }
         h->max_data_ctas = per_sm * prop.multiProcessorCount;
         h->pilot_wave = pilot_per_sm * prop.multiProcessorCount;
+        h->n_sms = prop.multiProcessorCount;
+        h->smem_optin = prop.sharedMemPerBlockOptin;
     }
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(h, e, "cudaStreamCreate"); return bail(LSMRC_ERR_CUDA); }
     for (int i = 0; i < lsmrc_ctx::kEvRing; ++i)
@@ -672,6 +838,14 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
     ops->fill_twiddles(tw.data());
     if ((e = cudaMalloc(&h->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc twiddles"); return bail(LSMRC_ERR_CUDA); }
     if ((e = cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { fail_cuda(h, e, "cudaMemcpy twiddles"); return bail(LSMRC_ERR_CUDA); }
+    if ((h->one_ops = find_oneshot_plan(cfg->fft_size)) != nullptr) {
+        const OneshotOps* oo = h->one_ops;
+        if ((e = oo->prepare((int)prop.sharedMemPerBlockOptin)) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute (one-launch kernel)"); return bail(LSMRC_ERR_CUDA); }
+        std::vector<float2> tw1((size_t)oo->twn);
+        oo->fill_twiddles(tw1.data());
+        if ((e = cudaMalloc(&h->d_one_tw, tw1.size() * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc twiddles"); return bail(LSMRC_ERR_CUDA); }
+        if ((e = cudaMemcpy(h->d_one_tw, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { fail_cuda(h, e, "cudaMemcpy twiddles"); return bail(LSMRC_ERR_CUDA); }
+    }
     if ((e = cudaMalloc(&h->d_pilot_bin, (size_t)h->K * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc pilot"); return bail(LSMRC_ERR_CUDA); }
     *out = h;
     return LSMRC_OK;
@@ -684,6 +858,7 @@ int lsmrc_destroy(lsmrc_handle h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (Lane& L : h->lanes) free_lane(L);
     cudaFree(h->d_tw);
+    cudaFree(h->d_one_tw);
     cudaFree(h->d_hit);
     cudaFree(h->d_pilot_bin);
     free_chan(h->dev_ch);
@@ -789,11 +964,37 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
     if (n_frames == 0) return LSMRC_OK;
     CK(h, cudaSetDevice(h->cfg.device));
-    int rc = ensure_lanes(h);
-    if (rc != LSMRC_OK) return rc;
     const lsmrc_config& c = h->cfg;
     const size_t nd = (size_t)(c.n_sym - 1);
     const size_t rx_fb = h->frame_elems * sizeof(float2);
+    // Latency path: a batch the one-launch kernel takes, in pinned host memory and small enough that
+    // PCIe latency rather than bandwidth decides, is processed in place -- the kernel loads the
+    // antenna-samples from and stores the results to the host buffers directly, so the call is one
+    // launch and one sync instead of a copy in, the kernels, and up to four copies out.
+    constexpr size_t kZeroCopyBytes = 512u << 10;
+    if (h->oneshot && h->zero_copy && h->one_ops && nd > 0 && rx_fb * (size_t)n_frames <= kZeroCopyBytes &&
+        h->one_ops->split(n_frames, c.n_sym - 1, c.n_ant, h->n_sms, h->smem_optin) > 0) {
+        void* a_rx = mapped_alias(h_rx);
+        void* a_cb = mapped_alias(h_combined);
+        void* a_bt = h_bits ? mapped_alias(h_bits) : nullptr;
+        void* a_hc = h_hconj ? mapped_alias(h_hconj) : nullptr;
+        void* a_hs = h_hsqrd ? mapped_alias(h_hsqrd) : nullptr;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(a_rx) | reinterpret_cast<uintptr_t>(a_cb) | reinterpret_cast<uintptr_t>(a_hc)) %
+                              sizeof(float2)) == 0 && reinterpret_cast<uintptr_t>(a_hs) % sizeof(float) == 0;
+        if (aligned && a_rx && a_cb && (!h_bits || a_bt) && (!h_hconj || a_hc) && (!h_hsqrd || a_hs)) {
+            cudaStream_t st = compute_stream(h);
+            int rc0 = ensure_chan(h, h->dev_ch, n_frames, st);
+            if (rc0 != LSMRC_OK) return rc0;
+            rc0 = launch_frames(h, st, static_cast<const float2*>(a_rx), n_frames, h->dev_ch, static_cast<float2*>(a_hc),
+                                static_cast<float*>(a_hs), static_cast<float2*>(a_cb), static_cast<uint8_t*>(a_bt), false);
+            if (rc0 != LSMRC_OK) return rc0;
+            CK(h, cudaStreamSynchronize(st));
+            h->zero_copy_calls++;
+            return LSMRC_OK;
+        }
+    }
+    int rc = ensure_lanes(h);
+    if (rc != LSMRC_OK) return rc;
     const size_t hc_fb = (size_t)c.n_ant * h->K * sizeof(float2);
     const size_t hs_fb = (size_t)h->K * sizeof(float);
     const size_t cb_fb = nd * h->K * sizeof(float2);
@@ -919,6 +1120,40 @@ static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L)
     return LSMRC_OK;
 }
 
+// Small frame in a pinned ring: the one-launch kernel reads the slots where they lie and writes the lane's pinned
+// result buffers directly -- no copy in, no copies out.  Returns 1 when it took the frame, 0 when the staged
+// path has to (pageable ring, large frame, one-launch kernel not applicable), < 0 on error.
+static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_first, const void* h_second, size_t slot_stride_bytes)
+{
+    const lsmrc_config& c = h->cfg;
+    constexpr size_t kZeroCopyBytes = 512u << 10;
+    if (!(h->oneshot && h->zero_copy && h->one_ops) || c.n_sym < 2 || h->frame_elems * sizeof(float2) > kZeroCopyBytes) return 0;
+    if (slot_stride_bytes % sizeof(float2) != 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(h_first) | reinterpret_cast<uintptr_t>(h_second)) % sizeof(float) != 0) return 0;
+    if (h->one_ops->split(1, c.n_sym - 1, c.n_ant, h->n_sms, h->smem_optin) <= 0) return 0;
+    void* a1 = mapped_alias(h_first);
+    void* a2 = (n_first < c.n_sym) ? mapped_alias(h_second) : nullptr;
+    if (!a1 || (n_first < c.n_sym && !a2)) return 0;
+    if (!L.a_comb) {
+        L.a_comb = static_cast<float2*>(mapped_alias(L.h_comb));
+        L.a_bits = static_cast<uint8_t*>(mapped_alias(L.h_bits));
+        L.a_hconj = static_cast<float2*>(mapped_alias(L.h_hconj));
+    }
+    if (!L.a_comb || !L.a_bits || !L.a_hconj) return 0;
+    RxLayout lay;
+    lay.sym_stride = (long long)(slot_stride_bytes / sizeof(float2));
+    lay.rx2 = static_cast<const float2*>(a2);
+    lay.split_sym = n_first;
+    lay.align4 = ((reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(a2)) % sizeof(float2)) != 0;
+    const int rc = launch_frames(h, L.st, static_cast<const float2*>(a1), 1, L.ch, L.a_hconj, nullptr, L.a_comb, L.a_bits, false, &lay);
+    if (rc != LSMRC_OK) return rc;
+    CK(h, cudaEventRecord(L.copied, L.st));  // the slots are free once the kernel has read them
+    CK(h, cudaEventRecord(L.done, L.st));
+    L.busy = true;
+    h->zero_copy_calls++;
+    return 1;
+}
+
 int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_t slot_stride_bytes)
 {
     if (!h || !h_slots) return fail(h, LSMRC_ERR_INVALID, "null argument");
@@ -929,10 +1164,11 @@ int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_
     if (rc != LSMRC_OK) return rc;
     Lane& L = h->lanes[(size_t)lane];
     const size_t slot_bytes = h->slot_elems * sizeof(float2);
+    if (slot_stride_bytes < slot_bytes) return fail(h, LSMRC_ERR_INVALID, "slot stride smaller than a slot");
+    if ((rc = ring_try_in_place(h, L, h_slots, h->cfg.n_sym, nullptr, slot_stride_bytes)) != 0) return rc < 0 ? rc : LSMRC_OK;
     if (slot_stride_bytes == slot_bytes) {
         CK(h, cudaMemcpyAsync(L.d_rx, h_slots, slot_bytes * h->cfg.n_sym, cudaMemcpyHostToDevice, L.st));
     } else {
-        if (slot_stride_bytes < slot_bytes) return fail(h, LSMRC_ERR_INVALID, "slot stride smaller than a slot");
         CK(h, cudaMemcpy2DAsync(L.d_rx, slot_bytes, h_slots, slot_stride_bytes, slot_bytes, (size_t)h->cfg.n_sym,
                                 cudaMemcpyHostToDevice, L.st));
     }
@@ -951,6 +1187,7 @@ int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void* h_first, int n
     if (rc != LSMRC_OK) return rc;
     Lane& L = h->lanes[(size_t)lane];
     const size_t slot_bytes = h->slot_elems * sizeof(float2);
+    if (n_first > 0 && (rc = ring_try_in_place(h, L, h_first, n_first, h_second, slot_bytes)) != 0) return rc < 0 ? rc : LSMRC_OK;
     if (n_first > 0) CK(h, cudaMemcpyAsync(L.d_rx, h_first, slot_bytes * n_first, cudaMemcpyHostToDevice, L.st));
     if (n_first < h->cfg.n_sym)
         CK(h, cudaMemcpyAsync(reinterpret_cast<char*>(L.d_rx) + slot_bytes * n_first, h_second,
@@ -1211,6 +1448,16 @@ int lsmrc_sync(lsmrc_handle h)
     for (Lane& L : h->lanes) CK(h, cudaStreamSynchronize(L.st));
     return LSMRC_OK;
 }
+int lsmrc_set_oneshot(lsmrc_handle h, int enabled)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    h->oneshot = enabled != 0;
+    h->zero_copy = enabled != 1;  // 1 = fused kernel but staged copies; any other non-zero value = both
+    return LSMRC_OK;
+}
+
+long long lsmrc_oneshot_count(lsmrc_handle h) { return h ? h->oneshot_calls : -1; }
+
 int lsmrc_set_timing(lsmrc_handle h, int enabled)
 {
     if (!h) return LSMRC_ERR_INVALID;
@@ -1246,8 +1493,10 @@ int lsmrc_describe_plan(lsmrc_handle h, char* buf, size_t buf_len)
 {
     if (!h || !buf || buf_len == 0) return LSMRC_ERR_INVALID;
     const PlanOps* o = h->ops;
-    std::snprintf(buf, buf_len, "N=%d P=%d R2=%d R3=%d teams=%d threads=%d smem=%zu minblocks=%d", o->N, o->P, o->R2,
-                  o->R3, o->teams, o->threads, o->smem, o->minb);
+    const OneshotOps* q = h->one_ops;
+    std::snprintf(buf, buf_len, "N=%d P=%d R2=%d R3=%d teams=%d threads=%d smem=%zu minblocks=%d; one-launch P=%d R2=%d R3=%d teams=%d calls=%lld in-place-host=%lld",
+                  o->N, o->P, o->R2, o->R3, o->teams, o->threads, o->smem, o->minb, q ? q->P : 0, q ? q->R2 : 0, q ? q->R3 : 0,
+                  q ? q->teams : 0, h->oneshot_calls, h->zero_copy_calls);
     return LSMRC_OK;
 }
 

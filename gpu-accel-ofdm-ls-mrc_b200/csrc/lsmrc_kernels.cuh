@@ -56,12 +56,17 @@
 
 namespace lsmrc {
 
-enum { MODE_PILOT = 0, MODE_DATA = 1, MODE_FFT = 2 };
+enum { MODE_PILOT = 0, MODE_DATA = 1, MODE_FFT = 2, MODE_ONESHOT = 3 };
 
 struct KernelParams {
     // input: antenna-samples, complex64.  element (f, s, a, n) at
     //   rx + f*frame_stride + s*sym_stride + a*ant_stride + n   (n includes the CP)
     const float2* rx;
+    // one-launch kernel only: symbols >= split_sym of the (single) frame continue at rx2 (a frame that
+    // wraps around the end of the shared-memory ring); split_sym >= n_sym when the frame is contiguous
+    const float2* rx2;
+    int split_sym;
+    int rx_align4;  // one-launch kernel only: samples are only 4-byte aligned (slots behind the ring's 12-byte header)
     long long frame_stride;
     long long sym_stride;
     int ant_stride;
@@ -262,6 +267,19 @@ __device__ __forceinline__ void row_load(float2 (&v)[PL::P], const float2* __res
     }
 }
 
+// the same for rows that are only 4-byte aligned: two 32-bit loads per sample
+template <class PL>
+__device__ __forceinline__ void row_load_align4(float2 (&v)[PL::P], const float2* __restrict__ x, int t)
+{
+    const float* xs = reinterpret_cast<const float*>(x);
+#pragma unroll
+    for (int n1 = 0; n1 < PL::P; ++n1) {
+        const float* q = xs + 2 * (n1 * PL::T + t);
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[n1].x) : "l"(q));
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[n1].y) : "l"(q + 1));
+    }
+}
+
 // Max-log LLRs of the Gray-mapped square QAM of demap_symbol(), the usual piecewise-linear form:
 //   bit 0/1 (sign bits):       4a*rho * re|im
 //   16-QAM bit 2/3:            4a*rho * (2a - |re|im|)
@@ -396,6 +414,69 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
     if constexpr (PL::NBUF == 1) team_sync<PL>(team);
 }
 
+// Epilogue of one (frame, data symbol) held by a team: normalise (cpuLS.hpp:364-367), reorder to
+// ascending frequency (cpuLS.hpp:135-149), demap, pack, optional LLRs.  acc[sl] is the MRC sum of
+// the bin the thread owns in slot sl; e_row[bin - 1] = sum_a |H|^2 (global, or shared when
+// E_SHARED).  Specialised on the QAM order so the demapper and the bit packing are straight-line
+// code.  s_idx: K bytes of team-private shared memory (aliases the team's tile).
+template <class PL, bool E_SHARED>
+__device__ __forceinline__ void mrc_finish(const KernelParams& p, const float2 (&acc)[PL::P], const float* __restrict__ e_row,
+                                           int f, int s, uint8_t* s_idx, bool valid, int t, int team)
+{
+    constexpr int N = PL::N, P = PL::P, T = PL::T, K = N - 1;
+    float2* out_row = p.combined + ((long long)f * p.n_sym_work + s) * K;
+    uint8_t* bits_row = p.bits ? p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes : nullptr;
+    float* llr_row = p.llr ? p.llr + ((long long)f * p.n_sym_work + s) * K * p.qam_bits : nullptr;
+    auto finish = [&](auto bconst) {
+        constexpr int b = decltype(bconst)::value;
+        float einv[P];
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) {
+            const int i = sl / PL::RL, j = sl % PL::RL;
+            const int bin = t + T * i + (N / PL::RL) * j;
+            const int idx = bin > 0 ? bin - 1 : 0;
+            einv[sl] = E_SHARED ? e_row[idx] : __ldg(e_row + idx);
+        }
+        team_sync<PL>(team);  // everyone is done reading the last tile before it is reused
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) {
+            const int i = sl / PL::RL, j = sl % PL::RL;
+            const int bin = t + T * i + (N / PL::RL) * j;
+            if (bin > 0) {
+                // one reciprocal, two multiplies (<= 2 ulp from the reference's two divisions,
+                // far inside the 1e-5 parity tolerance)
+                const float inv = __frcp_rn(einv[sl]);
+                const float2 o = make_float2(acc[sl].x * inv, acc[sl].y * inv);
+                const int pos = (bin < N / 2) ? (bin - 1 + N / 2) : (bin - N / 2);
+                if (valid) out_row[pos] = o;
+                s_idx[pos] = (uint8_t)demap_symbol(o.x, o.y, b);
+                if (llr_row != nullptr && valid) {
+                    float l[b];
+                    soft_symbol<b>(o.x, o.y, __fmul_rn(einv[sl], p.inv_noise_var), l);
+#pragma unroll
+                    for (int q = 0; q < b; ++q) llr_row[pos * b + q] = l[q];
+                }
+            }
+        }
+        if (bits_row != nullptr) {
+            team_sync<PL>(team);
+            for (int byte = t; byte < p.bits_row_bytes; byte += T) {
+                unsigned v8 = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int pos = byte * 8 + q;
+                    const int sym = pos / b, bit = pos - sym * b;
+                    if (sym < K) v8 |= ((s_idx[sym] >> bit) & 1u) << q;
+                }
+                if (valid) bits_row[byte] = (uint8_t)v8;
+            }
+        }
+    };
+    if (p.qam_bits == 2) finish(std::integral_constant<int, 2>{});
+    else if (p.qam_bits == 4) finish(std::integral_constant<int, 4>{});
+    else finish(std::integral_constant<int, 6>{});
+}
+
 template <class PL, int MODE, int MINB>
 __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelParams p)
 {
@@ -407,12 +488,14 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
     float2* s_hring = smem + PL::TWN;
     float2* s_tiles = smem + PL::TWN + PL::HRING;
 
-    for (int i = threadIdx.x; i < PL::TWN; i += PL::THREADS) smem[i] = p.twiddles[i];
-    __syncthreads();
-
     const int team = threadIdx.x / T;
     const int t = threadIdx.x % T;
     float2* my_tiles = s_tiles + team * (PL::NBUF * PL::TILE);
+
+    if constexpr (MODE != MODE_ONESHOT) {  // (the one-shot mode issues its first row loads before this copy)
+        for (int i = threadIdx.x; i < PL::TWN; i += PL::THREADS) smem[i] = p.twiddles[i];
+        __syncthreads();
+    }
 
     if constexpr (MODE == MODE_FFT) {
         // stand-alone batched transform (gpuLS::batchedFFT, gpuLS.cu:343-349): p.rx holds
@@ -516,6 +599,177 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                 }
             }
         }
+    } else if constexpr (MODE == MODE_ONESHOT) {
+        // Whole frames in ONE launch, for calls that are launch-latency bound (a single small frame,
+        // BASELINE config c5): CTA (f, g) first estimates the channel of frame f itself -- all its
+        // teams share the A pilot rows, conj(H) and sum|H|^2 stay in shared memory -- and then
+        // combines its own `slots` data symbols against them.  Every CTA of a frame repeats the
+        // pilot work (1/S of the frame, a round or two of row FFTs) in exchange for dropping the
+        // second launch and the global round trip of H; CTA g == 0 also writes H to global memory
+        // for callers that read it back.  The host picks this mode only when the whole batch is
+        // one partial wave of CTAs and A*N conj(H) values fit in shared memory.
+        float2* s_h = s_tiles + PL::TEAMS * PL::NBUF * PL::TILE;                 // [A][N]
+        float* s_esum = reinterpret_cast<float*>(s_h + (size_t)p.n_ant * N);     // [N], entry 0 unused
+        const int AS = p.ant_split;           // teams sharing one (frame, symbol)
+        const int slots = PL::TEAMS / AS;     // data symbols per CTA
+        const int aj = team % AS;
+        const int groups = (p.n_sym_work + slots - 1) / slots;
+        const int f = blockIdx.x / groups;
+        const int g = blockIdx.x % groups;
+        const bool writer = (g == 0);
+        const float2* xf = p.rx + (long long)f * p.frame_stride + p.cp;  // symbol 0 = pilot, data from p.first_sym
+        int s = g * slots + team / AS;
+        bool valid = s < p.n_sym_work;
+        if (!valid) s = p.n_sym_work - 1;
+        const int sd = p.first_sym + s;
+        const float2* xd = (sd < p.split_sym) ? xf + (long long)sd * p.sym_stride
+                                              : p.rx2 + p.cp + (long long)(sd - p.split_sym) * p.sym_stride;
+
+        // issue every load the first rounds need before anything waits: pilot row, first data row
+        // (registers when they are cheap, L2 otherwise), pilot values, twiddles
+        constexpr bool EARLY = (P <= 16);
+        float2 v[P];
+        float2 vd[EARLY ? P : 1];
+        auto load_row = [&](auto& dst, const float2* src) {
+            if (p.rx_align4) row_load_align4<PL>(dst, src, t);
+            else row_load<PL>(dst, src, t);
+        };
+        {
+            const int a0 = team < p.n_ant ? team : p.n_ant - 1;
+            load_row(v, xf + (long long)a0 * p.ant_stride);
+            const int ad = aj < p.n_ant ? aj : p.n_ant - 1;
+            if constexpr (EARLY) load_row(vd, xd + (long long)ad * p.ant_stride);
+            else prefetch_row<T, false>(xd + (long long)ad * p.ant_stride, N, t);
+        }
+        float e[P];
+        float2 xp[P];
+        float xden[P];
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) {
+            const int i = sl / PL::RL, j = sl % PL::RL;
+            const int bin = t + T * i + (N / PL::RL) * j;
+            e[sl] = 0.f;
+            xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
+        }
+        for (int i = threadIdx.x; i < PL::TWN; i += PL::THREADS) smem[i] = p.twiddles[i];
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) xden[sl] = 1.0f / (xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y);
+        __syncthreads();
+
+        // ---- channel estimate (same arithmetic as MODE_PILOT with one antenna group) ----
+        float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+        float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
+        const int n_iter = (p.n_ant + PL::TEAMS - 1) / PL::TEAMS;
+        for (int it = 0; it < n_iter; ++it) {
+            const int a_raw = it * PL::TEAMS + team;
+            const bool a_ok = a_raw < p.n_ant;
+            const int a = a_ok ? a_raw : p.n_ant - 1;
+            float2* tile = my_tiles + (PL::NBUF == 2 ? (it & 1) * PL::TILE : 0);
+            if (it > 0) load_row(v, xf + (long long)a * p.ant_stride);
+            float2* sh_row = s_h + (size_t)a * N;
+            float2* hw_row = hw_frame + (long long)a * N;
+            float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
+            row_fft<PL>(v, nullptr, tile, s_tw1, s_tw2, t, team, [&](int sl, int bin, float2 z) {
+                const float2 X = xp[sl];
+                const float re = (z.x * X.x + z.y * X.y) * xden[sl];
+                const float im = (z.y * X.x - z.x * X.y) * xden[sl];
+                if (a_ok) {
+                    const float2 hc = (bin > 0) ? make_float2(re, -im) : make_float2(0.f, 0.f);
+                    sh_row[bin] = hc;
+                    if (writer) {
+                        hw_row[bin] = hc;
+                        if (bin > 0 && hc_row) hc_row[bin - 1] = hc;
+                    }
+                    if (bin > 0) e[sl] += re * re + im * im;
+                }
+            });
+        }
+        // sum the energy partials over the teams: the teams of a warp by shuffles, then the warps
+        // (or the teams, when a team is a warp or more) through shared memory
+        constexpr int TPW = (T < 32) ? 32 / T : 1;                        // teams per warp
+        constexpr int NPART = (T < 32) ? (PL::THREADS + 31) / 32 : PL::TEAMS;
+        if constexpr (TPW > 1) {
+#pragma unroll
+            for (int off = T; off < 32; off <<= 1) {
+#pragma unroll
+                for (int sl = 0; sl < P; ++sl) e[sl] += __shfl_xor_sync(0xffffffffu, e[sl], off);
+            }
+        }
+        __syncthreads();
+        float* s_e = reinterpret_cast<float*>(s_tiles);  // [NPART][N]
+        if (team % TPW == 0) {
+            const int part = team / TPW;
+#pragma unroll
+            for (int sl = 0; sl < P; ++sl) {
+                const int i = sl / PL::RL, j = sl % PL::RL;
+                const int bin = t + T * i + (N / PL::RL) * j;
+                s_e[part * N + bin] = e[sl];
+            }
+        }
+        __syncthreads();
+        for (int bin = 1 + threadIdx.x; bin < N; bin += PL::THREADS) {
+            float acc = s_e[bin];
+#pragma unroll
+            for (int pt = 1; pt < NPART; ++pt) acc += s_e[pt * N + bin];
+            s_esum[bin] = acc;
+            if (writer) p.hsqrd[(long long)f * K + bin - 1] = acc;
+        }
+        __syncthreads();
+
+        // ---- data symbols of this CTA against the shared-memory channel ----
+        float2 acc[P];
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) acc[sl] = make_float2(0.f, 0.f);
+        const int n_rounds = (p.n_ant + AS - 1) / AS;
+        for (int rd = 0; rd < n_rounds; ++rd) {
+            const int a_raw = rd * AS + aj;
+            const bool a_ok = a_raw < p.n_ant;
+            const int a = a_ok ? a_raw : p.n_ant - 1;
+            float2* tile = my_tiles + (PL::NBUF == 2 ? (rd & 1) * PL::TILE : 0);
+            if (EARLY && rd == 0) {
+#pragma unroll
+                for (int n1 = 0; n1 < P; ++n1) v[n1] = vd[EARLY ? n1 : 0];
+            } else {
+                load_row(v, xd + (long long)a * p.ant_stride);
+            }
+            if (a_raw + AS < p.n_ant) prefetch_row<T, false>(xd + (long long)(a_raw + AS) * p.ant_stride, N, t);
+            const float2* h_row = s_h + (size_t)a * N;
+            row_fft<PL>(v, nullptr, tile, s_tw1, s_tw2, t, team, [&](int sl, int bin, float2 y) {
+                if (a_ok) acc[sl] = cmac(acc[sl], h_row[bin], y);
+            });
+        }
+        if (AS > 1) {
+            // add the antenna slices: teams that share a warp by shuffles, the rest through shared memory
+            const int G = AS < TPW ? AS : TPW;  // teams combined inside a warp
+            if constexpr (TPW > 1) {
+                for (int off = T; off < T * G; off <<= 1) {
+#pragma unroll
+                    for (int sl = 0; sl < P; ++sl) {
+                        acc[sl].x += __shfl_xor_sync(0xffffffffu, acc[sl].x, off);
+                        acc[sl].y += __shfl_xor_sync(0xffffffffu, acc[sl].y, off);
+                    }
+                }
+            }
+            const int rem = AS / G;  // partial sums left per (frame, symbol)
+            if (rem > 1) {
+                float2* red = s_tiles;  // [TEAMS / G][P*T], aliases the tiles (all teams are past their last row)
+                __syncthreads();
+                if (team % G == 0) {
+#pragma unroll
+                    for (int sl = 0; sl < P; ++sl) red[((team / G) * P + sl) * T + t] = acc[sl];
+                }
+                __syncthreads();
+                if (aj == 0) {
+                    for (int jj = 1; jj < rem; ++jj) {
+#pragma unroll
+                        for (int sl = 0; sl < P; ++sl) acc[sl] = cadd(acc[sl], red[((team / G + jj) * P + sl) * T + t]);
+                    }
+                }
+                __syncthreads();
+            }
+            valid = valid && (aj == 0);
+        }
+        mrc_finish<PL, true>(p, acc, s_esum + 1, f, s, reinterpret_cast<uint8_t*>(my_tiles), valid, t, team);
     } else {
         // Persistent CTAs: the grid is sized to the SM count and every CTA pulls work items from a
         // global ticket counter (dynamic, so faster SMs take more), so the twiddle table, the ring
@@ -671,60 +925,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             valid = valid && (aj == 0);
         }
 
-        // epilogue: normalise (cpuLS.hpp:364-367), reorder (cpuLS.hpp:135-149), demap, pack.
-        // Specialised on the QAM order so the demapper and the bit packing are straight-line code.
-        const float* e_row = p.hsqrd + (long long)f * K;
-        float2* out_row = p.combined + ((long long)f * p.n_sym_work + s) * K;
-        uint8_t* s_idx = reinterpret_cast<uint8_t*>(my_tiles);
-        uint8_t* bits_row = p.bits ? p.bits + ((long long)f * p.n_sym_work + s) * p.bits_row_bytes : nullptr;
-        float* llr_row = p.llr ? p.llr + ((long long)f * p.n_sym_work + s) * K * p.qam_bits : nullptr;
-        auto finish = [&](auto bconst) {
-            constexpr int b = decltype(bconst)::value;
-            float einv[P];
-#pragma unroll
-            for (int sl = 0; sl < P; ++sl) {
-                const int i = sl / PL::RL, j = sl % PL::RL;
-                const int bin = t + T * i + (N / PL::RL) * j;
-                einv[sl] = __ldg(e_row + (bin > 0 ? bin - 1 : 0));
-            }
-            team_sync<PL>(team);  // everyone is done reading the last tile before it is reused
-#pragma unroll
-            for (int sl = 0; sl < P; ++sl) {
-                const int i = sl / PL::RL, j = sl % PL::RL;
-                const int bin = t + T * i + (N / PL::RL) * j;
-                if (bin > 0) {
-                    // one reciprocal, two multiplies (<= 2 ulp from the reference's two divisions,
-                    // far inside the 1e-5 parity tolerance)
-                    const float inv = __frcp_rn(einv[sl]);
-                    const float2 o = make_float2(acc[sl].x * inv, acc[sl].y * inv);
-                    const int pos = (bin < N / 2) ? (bin - 1 + N / 2) : (bin - N / 2);
-                    if (valid) out_row[pos] = o;
-                    s_idx[pos] = (uint8_t)demap_symbol(o.x, o.y, b);
-                    if (llr_row != nullptr && valid) {
-                        float l[b];
-                        soft_symbol<b>(o.x, o.y, __fmul_rn(einv[sl], p.inv_noise_var), l);
-#pragma unroll
-                        for (int q = 0; q < b; ++q) llr_row[pos * b + q] = l[q];
-                    }
-                }
-            }
-            if (bits_row != nullptr) {
-                team_sync<PL>(team);
-                for (int byte = t; byte < p.bits_row_bytes; byte += T) {
-                    unsigned v8 = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int pos = byte * 8 + q;
-                        const int sym = pos / b, bit = pos - sym * b;
-                        if (sym < K) v8 |= ((s_idx[sym] >> bit) & 1u) << q;
-                    }
-                    if (valid) bits_row[byte] = (uint8_t)v8;
-                }
-            }
-        };
-        if (p.qam_bits == 2) finish(std::integral_constant<int, 2>{});
-        else if (p.qam_bits == 4) finish(std::integral_constant<int, 4>{});
-        else finish(std::integral_constant<int, 6>{});
+        mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(my_tiles), valid, t, team);
         team_sync<PL>(team);  // the byte buffer aliases the tile the next item writes
         }  // work items
     }

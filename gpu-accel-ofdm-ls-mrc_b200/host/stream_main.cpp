@@ -97,7 +97,9 @@ int main(int argc, char** argv)
     for (int f = (frames > n_lanes ? frames - n_lanes : 0); f < frames; ++f) collect(f % n_lanes);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const double samples = (double)frames * syms * rows * (cols + cp);
-    printf("{\"frames\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f}\n",
-           frames, dt, frames / dt, samples / dt, samples * 8.0 / dt / 1e9);
+    char plan[256] = "";
+    lsmrc_describe_plan(ls.handle, plan, sizeof plan);
+    printf("{\"frames\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f, \"plan\": \"%s\"}\n",
+           frames, dt, frames / dt, samples / dt, samples * 8.0 / dt / 1e9, plan);
     return 0;
 }

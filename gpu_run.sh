@@ -1,3 +1,3 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/quick_bench.py --config c2 --frames 256 --iters 4 2>&1 | tail -1
+python -m pytest tests -m gpu -x -q 2>&1 | grep -v "^$" | tail -12
+gpu-accel-ofdm-ls-mrc_b200/host/bin/latency_main --launches 3000

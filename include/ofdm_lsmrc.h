@@ -181,6 +181,14 @@ int lsmrc_host_register(lsmrc_handle h, void *h_ptr, size_t bytes); /* pin an ex
 int lsmrc_host_unregister(lsmrc_handle h, void *h_ptr);
 int lsmrc_set_stream(lsmrc_handle h, void *cuda_stream); /* run device-resident calls on a caller stream (NULL = own) */
 int lsmrc_sync(lsmrc_handle h);
+/* Launch policy for whole-frame calls.  A batch small enough to be launch-latency bound (a single small frame,
+ * BASELINE config c5) runs as ONE fused kernel -- channel estimate and data symbols together, H kept in shared
+ * memory -- instead of the pilot + data pair; lsmrc_demod_frames_host additionally lets that kernel read and write
+ * PINNED host buffers in place (no staging copies) when the batch is at most 512 KiB.  enabled: 2 (default) both,
+ * 1 fused kernel but staged copies, 0 always the two-kernel path.  Results agree to rounding. */
+int lsmrc_set_oneshot(lsmrc_handle h, int enabled);
+/* whole-frame calls served by the one-launch kernel so far */
+long long lsmrc_oneshot_count(lsmrc_handle h);
 
 /* ---- instrumentation (replaces the clock() timers of ShMemSymBuff_gpu.hpp:113-257) --- */
 /* CUDA-event time of the pilot and data kernels of the most recent lsmrc_demod_frames_device

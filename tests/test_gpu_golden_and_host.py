@@ -70,9 +70,12 @@ def test_ring_fed_cpp_consumers_match_oracle(ofdm, oracle, host_bins, tmp_path, 
     d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=10.0, seed=1235)
     ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
     ring = S + 1 if (consumer == "gpuLS_main" and not extra) else 4 * S + 1
-    comb, bits, _ = _run_ring(host_bins, tmp_path, consumer, extra, d, A, N, C, S, b, F, ring)
+    comb, bits, out = _run_ring(host_bins, tmp_path, consumer, extra, d, A, N, C, S, b, F, ring)
     assert_close(comb, ref["combined"], f"{consumer} combined")
     assert np.array_equal(bits, ref["bits"])
+    if consumer == "stream_main":
+        # small frames in the pinned ring are read in place by the one-launch kernel, ring wrap included
+        assert f"in-place-host={F}" in out, out
 
 
 def test_stream_main_config3_dims(ofdm, oracle, host_bins, tmp_path):

@@ -112,3 +112,80 @@ def test_errors_are_reported(ofdm):
         with pytest.raises(ofdm.LsmrcError):
             rx.demod_numpy(d["rx"])  # no pilot yet
         assert rx.set_pilot_file("/nonexistent/Pilots.dat") == 1  # reference fallback 0.707+0.707i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(16, 64, 16, 16, 2, 1), (4, 64, 16, 16, 2, 2), (24, 64, 16, 5, 6, 1), (16, 128, 32, 9, 4, 1), (32, 128, 32, 3, 2, 2),
+                                  (8, 256, 64, 6, 4, 2), (12, 512, 128, 4, 6, 1), (6, 1024, 64, 5, 4, 1),
+                                  (3, 2048, 144, 3, 2, 1), (2, 4096, 288, 3, 6, 1)])
+def test_one_launch_mode_matches_oracle_and_two_kernel_path(ofdm, oracle, dims):
+    """Launch-latency-bound batches (BASELINE c5: one small frame per call) run as ONE fused kernel; it must
+    give the oracle's results and agree with the pilot + data kernel pair on the same input."""
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=18.0, seed=5, channel="unit" if A == 1 else "rayleigh")
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    dev = torch.device("cuda:0")
+    rx = torch.view_as_real(torch.from_numpy(d["rx"]).to(dev)).contiguous()
+    out = {}
+    for mode in (1, 0):
+        comb = torch.zeros((F, S - 1, K, 2), device=dev)
+        bits = torch.zeros((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+        hconj = torch.zeros((F, A, K, 2), device=dev)
+        hsq = torch.zeros((F, K), device=dev)
+        with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+            r.set_pilot(d["pilot_asc"])
+            r.set_oneshot(mode)
+            r.demod_frames_device(rx, F, comb, bits, hconj, hsq)
+            r.sync()
+            assert (r.oneshot_count() > 0) == (mode == 1), (mode, r.describe_plan())
+        out[mode] = (torch.view_as_complex(comb).cpu().numpy(), bits.cpu().numpy(), torch.view_as_complex(hconj).cpu().numpy(),
+                     hsq.cpu().numpy())
+        assert_close(out[mode][2], ref["hconj"], "Hconj", tol=1e-5)
+        assert_close(out[mode][3], ref["hsqrd"], "Hsqrd", tol=1e-5)
+        assert_close(out[mode][0], ref["combined"], "combined", tol=1e-5)
+        if not np.array_equal(out[mode][1], ref["bits"]):
+            n_diff = int(np.unpackbits(out[mode][1] ^ ref["bits"]).sum())
+            pytest.fail(f"mode {mode}: {n_diff} demapped bits differ (closest oracle symbol is "
+                        f"{threshold_margin(ref['combined'], b):.3e} from a threshold)")
+    assert_close(out[1][0], out[0][0], "one-launch vs two-kernel combined", tol=2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(16, 64, 16, 16, 2, 1), (4, 64, 16, 16, 2, 3), (8, 256, 32, 5, 6, 1)])
+@pytest.mark.parametrize("how", ["host_alloc", "host_register"])
+def test_small_pinned_frames_are_processed_in_place(ofdm, oracle, dims, how):
+    """lsmrc_demod_frames_host on a small batch in pinned memory: the one-launch kernel reads the samples from
+    and writes every result to the host buffers directly (no staging copies); same results as the oracle."""
+    A, N, C, S, b, F = dims
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=SNR[b], seed=23)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    with ofdm.LsMrcReceiver(A, N, C, S, b, max_frames=F) as r:
+        r.set_pilot(d["pilot_asc"])
+        shapes = {"rx": (d["rx"].shape, np.complex64), "comb": ((F, S - 1, K), np.complex64),
+                  "bits": ((F, S - 1, (K * b + 7) // 8), np.uint8), "hconj": ((F, A, K), np.complex64), "hsq": ((F, K), np.float32)}
+        if how == "host_alloc":
+            buf = {k: r.pinned_array(*v) for k, v in shapes.items()}
+        else:
+            buf = {k: np.zeros(*v) for k, v in shapes.items()}
+            for v in buf.values():
+                r.host_register(v)
+        buf["rx"][...] = d["rx"]
+        for k in ("comb", "bits", "hconj", "hsq"):
+            buf[k][...] = 0
+        r.demod_frames_host(buf["rx"], F, buf["comb"], buf["bits"], buf["hconj"], buf["hsq"])
+        assert "in-place-host=1" in r.describe_plan(), r.describe_plan()
+        got = {k: np.array(v) for k, v in buf.items()}
+        # pageable buffers take the staged path and must agree
+        out2 = r.demod_numpy(d["rx"])
+        if how == "host_register":
+            for v in buf.values():
+                r.host_unregister(v)
+    assert_close(got["hconj"], ref["hconj"], "Hconj")
+    assert_close(got["hsq"], ref["hsqrd"], "sum|H|^2")
+    assert_close(got["comb"], ref["combined"], "combined")
+    assert np.array_equal(got["bits"], ref["bits"]) or threshold_margin(ref["combined"], b) < 1e-5
+    assert_close(out2["combined"], got["comb"], "staged vs in place", tol=2e-6)
