@@ -502,10 +502,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e_err = int(np.unpackbits(h_bits[:1] ^ got[:1].numpy()).sum()) if Fe >= 1 else 0
+        # the host path leaves the cyclic prefix behind (strided H2D copy): count the bytes actually moved
+        strip = "h2d=strip-cp" in rcv.describe_plan()
+        h2d = int(h_rx.nbytes * cfg.fft_size // (cfg.fft_size + cfg.cp_len)) if strip else int(h_rx.nbytes)
         e2e = {"value": world * Fe * n_e2e * cfg.antenna_samples_per_frame / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_rx.nbytes), "d2h_bytes_per_step": int(h_comb.nbytes + h_bits.nbytes),
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_comb.nbytes + h_bits.nbytes),
                "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e, "api": "lsmrc_demod_frames_host (pinned host buffers, 3 lanes)",
-               "h2d_gbs": world * h_rx.nbytes * n_e2e / dt / 1e9, "bit_mismatch_vs_device_path": e2e_err}
+               "h2d_gbs": world * h2d * n_e2e / dt / 1e9, "host_input_bytes_per_step": int(h_rx.nbytes),
+               "h2d_copy": "strided, cyclic prefix left on the host" if strip else "whole slots",
+               "bit_mismatch_vs_device_path": e2e_err}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

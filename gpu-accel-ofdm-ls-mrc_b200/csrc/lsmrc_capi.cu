@@ -13,6 +13,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -377,6 +378,8 @@ struct lsmrc_ctx {
     long long zero_copy_calls = 0;  // ... of which on pinned host buffers in place
     bool oneshot = true;
     bool zero_copy = true;        // one-launch kernel reads/writes pinned host buffers in place (small frames)
+    bool h2d_strip_cp = true;     // lsmrc_demod_frames_host: strided H2D copy that leaves the cyclic prefix behind
+    size_t h2d_strip_min_row = 4096;  // ... for rows of at least this many bytes (LSMRC_H2D_STRIP_MIN_ROW, 0 = off)
     float2* d_tw = nullptr;
     float2* d_pilot_bin = nullptr;
     bool have_pilot = false;
@@ -542,6 +545,7 @@ int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, fl
 // where the symbols of ONE frame sit when they are not a dense [S][A][N+C] block (ring slots read in place)
 struct RxLayout {
     long long sym_stride;  // complex elements between consecutive symbols
+    bool dense = false;    // the cyclic prefix was dropped on the way in: rows of N samples, [F][S][A][N]
     const float2* rx2;     // symbols >= split_sym continue here (ring wrap); nullptr = contiguous
     int split_sym;
     int align4;            // slots are 4- but not 8-byte aligned (the reference ring's 12-byte header)
@@ -554,6 +558,13 @@ int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frame
 {
     KernelParams p = base_params(h);
     p.rx = d_rx;
+    if (lay && lay->dense) {
+        p.cp = 0;
+        p.ant_stride = h->cfg.fft_size;
+        p.sym_stride = (long long)h->cfg.n_ant * h->cfg.fft_size;
+        p.frame_stride = p.sym_stride * h->cfg.n_sym;
+        lay = nullptr;
+    }
     if (lay) {
         p.sym_stride = lay->sym_stride;
         p.rx_align4 = lay->align4;
@@ -838,6 +849,11 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
     ops->fill_twiddles(tw.data());
     if ((e = cudaMalloc(&h->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc twiddles"); return bail(LSMRC_ERR_CUDA); }
     if ((e = cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { fail_cuda(h, e, "cudaMemcpy twiddles"); return bail(LSMRC_ERR_CUDA); }
+    if (const char* ev = std::getenv("LSMRC_H2D_STRIP_MIN_ROW")) {  // tuning/A-B knob
+        const long v = std::atol(ev);
+        h->h2d_strip_cp = v > 0;
+        if (v > 0) h->h2d_strip_min_row = (size_t)v;
+    }
     if ((h->one_ops = find_oneshot_plan(cfg->fft_size)) != nullptr) {
         const OneshotOps* oo = h->one_ops;
         if ((e = oo->prepare((int)prop.sharedMemPerBlockOptin)) != cudaSuccess) { fail_cuda(h, e, "cudaFuncSetAttribute (one-launch kernel)"); return bail(LSMRC_ERR_CUDA); }
@@ -1006,14 +1022,25 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     pin_cb.pin(h_combined, cb_fb * n_frames);
     pin_bt.pin(h_bits, bt_fb * n_frames);
 
+    // strided H2D that skips the cyclic prefix: worth it when rows are long enough for the copy engine
+    const bool strip_cp = h->h2d_strip_cp && c.cp_len > 0 && (size_t)c.fft_size * sizeof(float2) >= h->h2d_strip_min_row;
     int chunk_idx = 0;
     for (int f0 = 0; f0 < n_frames; f0 += c.max_frames, ++chunk_idx) {
         const int nf = (n_frames - f0 < c.max_frames) ? (n_frames - f0) : c.max_frames;
         Lane& L = h->lanes[(size_t)chunk_idx % h->lanes.size()];
         const char* src = static_cast<const char*>(h_rx) + (size_t)f0 * rx_fb;
-        CK(h, cudaMemcpyAsync(L.d_rx, src, rx_fb * nf, cudaMemcpyHostToDevice, L.st));
+        RxLayout dense_lay{};
+        dense_lay.dense = true;
+        if (strip_cp) {
+            // the cyclic prefix is never used: leave it on the host (C/(N+C) of the PCIe bytes)
+            const size_t row = (size_t)c.fft_size * sizeof(float2), pitch = (size_t)(c.fft_size + c.cp_len) * sizeof(float2);
+            CK(h, cudaMemcpy2DAsync(L.d_rx, row, src + (size_t)c.cp_len * sizeof(float2), pitch, row,
+                                    (size_t)nf * c.n_sym * c.n_ant, cudaMemcpyHostToDevice, L.st));
+        } else {
+            CK(h, cudaMemcpyAsync(L.d_rx, src, rx_fb * nf, cudaMemcpyHostToDevice, L.st));
+        }
         rc = launch_frames(h, L.st, L.d_rx, nf, L.ch, h_hconj ? L.d_hconj : nullptr, nullptr, L.d_comb,
-                           h_bits ? L.d_bits : nullptr, false);
+                           h_bits ? L.d_bits : nullptr, false, strip_cp ? &dense_lay : nullptr);
         if (rc != LSMRC_OK) return rc;
         if (nd > 0)
             CK(h, cudaMemcpyAsync(static_cast<char*>(h_combined) + (size_t)f0 * cb_fb, L.d_comb, cb_fb * nf,
@@ -1141,6 +1168,7 @@ static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_f
     }
     if (!L.a_comb || !L.a_bits || !L.a_hconj) return 0;
     RxLayout lay;
+    lay.dense = false;
     lay.sym_stride = (long long)(slot_stride_bytes / sizeof(float2));
     lay.rx2 = static_cast<const float2*>(a2);
     lay.split_sym = n_first;
@@ -1494,9 +1522,10 @@ int lsmrc_describe_plan(lsmrc_handle h, char* buf, size_t buf_len)
     if (!h || !buf || buf_len == 0) return LSMRC_ERR_INVALID;
     const PlanOps* o = h->ops;
     const OneshotOps* q = h->one_ops;
-    std::snprintf(buf, buf_len, "N=%d P=%d R2=%d R3=%d teams=%d threads=%d smem=%zu minblocks=%d; one-launch P=%d R2=%d R3=%d teams=%d calls=%lld in-place-host=%lld",
+    std::snprintf(buf, buf_len, "N=%d P=%d R2=%d R3=%d teams=%d threads=%d smem=%zu minblocks=%d; one-launch P=%d R2=%d R3=%d teams=%d calls=%lld in-place-host=%lld; h2d=%s",
                   o->N, o->P, o->R2, o->R3, o->teams, o->threads, o->smem, o->minb, q ? q->P : 0, q ? q->R2 : 0, q ? q->R3 : 0,
-                  q ? q->teams : 0, h->oneshot_calls, h->zero_copy_calls);
+                  q ? q->teams : 0, h->oneshot_calls, h->zero_copy_calls,
+                  (h->h2d_strip_cp && h->cfg.cp_len > 0 && (size_t)h->cfg.fft_size * sizeof(float2) >= h->h2d_strip_min_row) ? "strip-cp" : "whole-slots");
     return LSMRC_OK;
 }
 
