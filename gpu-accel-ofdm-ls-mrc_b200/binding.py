@@ -61,6 +61,8 @@ ABI = {
     "lsmrc_host_unregister": (c_int, [c_void_p, c_void_p]),
     "lsmrc_set_stream": (c_int, [c_void_p, c_void_p]),
     "lsmrc_sync": (c_int, [c_void_p]),
+    "lsmrc_estimate_noise_var": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lsmrc_llr_from_combined": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lsmrc_set_timing": (c_int, [c_void_p, c_int]),
     "lsmrc_set_oneshot": (c_int, [c_void_p, c_int]),
     "lsmrc_oneshot_count": (ctypes.c_longlong, [c_void_p]),
@@ -182,6 +184,12 @@ class LsMrcReceiver:
     def demod_frames_device_soft(self, d_rx, n_frames, d_combined, d_llr, noise_var, d_bits=None):
         self._ck(self.lib.lsmrc_demod_frames_device_soft(self.h, _ptr(d_rx), n_frames, _ptr(d_combined), _ptr(d_bits),
                                                          _ptr(d_llr), noise_var))
+
+    def estimate_noise_var(self, d_combined, d_hsqrd, n_frames, d_noise_var):
+        self._ck(self.lib.lsmrc_estimate_noise_var(self.h, _ptr(d_combined), _ptr(d_hsqrd), n_frames, _ptr(d_noise_var)))
+
+    def llr_from_combined(self, d_combined, d_hsqrd, d_noise_var, n_frames, d_llr):
+        self._ck(self.lib.lsmrc_llr_from_combined(self.h, _ptr(d_combined), _ptr(d_hsqrd), _ptr(d_noise_var), n_frames, _ptr(d_llr)))
 
     def demod_frames_host(self, h_rx, n_frames, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
         self._ck(self.lib.lsmrc_demod_frames_host(self.h, _ptr(h_rx), n_frames, _ptr(h_hconj), _ptr(h_hsqrd),

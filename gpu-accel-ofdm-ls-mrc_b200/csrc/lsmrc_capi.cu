@@ -400,6 +400,8 @@ struct lsmrc_ctx {
     bool have_channel = false;
     std::vector<Lane> lanes;
     unsigned long long* d_hit = nullptr;  // frame-sync first-hit key
+    float* d_noise_part = nullptr;        // [frames][S-1] row partials of the noise estimator
+    size_t noise_part_rows = 0;
     float* soft_llr = nullptr;            // set for the duration of a *_soft call
     float soft_inv_noise = 1.f;
     bool timing = false;
@@ -875,6 +877,7 @@ int lsmrc_destroy(lsmrc_handle h)
     for (Lane& L : h->lanes) free_lane(L);
     cudaFree(h->d_tw);
     cudaFree(h->d_one_tw);
+    cudaFree(h->d_noise_part);
     cudaFree(h->d_hit);
     cudaFree(h->d_pilot_bin);
     free_chan(h->dev_ch);
@@ -970,6 +973,58 @@ int lsmrc_demod_frames_device_soft(lsmrc_handle h, const void* d_rx, int n_frame
                                  static_cast<float2*>(d_combined), static_cast<uint8_t*>(d_bits), h->timing);
     h->soft_llr = nullptr;
     return rc;
+}
+
+int lsmrc_estimate_noise_var(lsmrc_handle h, const void* d_combined, const void* d_hsqrd, int n_frames, void* d_noise_var)
+{
+    if (!h || !d_combined || !d_hsqrd || !d_noise_var) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_frames < 0) return fail(h, LSMRC_ERR_INVALID, "n_frames < 0");
+    const int nd = h->cfg.n_sym - 1;
+    if (nd < 1) return fail(h, LSMRC_ERR_STATE, "no data symbols in a frame");
+    if (n_frames == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = compute_stream(h);
+    const size_t rows = (size_t)n_frames * nd;
+    if (rows > h->noise_part_rows) {
+        CK(h, cudaStreamSynchronize(st));
+        cudaFree(h->d_noise_part);
+        h->d_noise_part = nullptr;
+        h->noise_part_rows = 0;
+        CK(h, cudaMalloc(&h->d_noise_part, rows * sizeof(float)));
+        h->noise_part_rows = rows;
+    }
+    k_noise_rows<<<(unsigned)rows, 256, 0, st>>>(static_cast<const float2*>(d_combined), static_cast<const float*>(d_hsqrd), h->K, nd,
+                                                 h->cfg.qam_bits, h->d_noise_part);
+    k_noise_frames<<<(unsigned)((n_frames + 7) / 8), 256, 0, st>>>(h->d_noise_part, nd, h->K, n_frames, static_cast<float*>(d_noise_var));
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+int lsmrc_llr_from_combined(lsmrc_handle h, const void* d_combined, const void* d_hsqrd, const void* d_noise_var, int n_frames,
+                            void* d_llr)
+{
+    if (!h || !d_combined || !d_hsqrd || !d_noise_var || !d_llr) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_frames < 0) return fail(h, LSMRC_ERR_INVALID, "n_frames < 0");
+    const int nd = h->cfg.n_sym - 1;
+    if (nd < 1) return fail(h, LSMRC_ERR_STATE, "no data symbols in a frame");
+    if (n_frames == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = compute_stream(h);
+    const long long n_sym = (long long)n_frames * nd * h->K;
+    const float2* y = static_cast<const float2*>(d_combined);
+    const float* e = static_cast<const float*>(d_hsqrd);
+    const float* nv = static_cast<const float*>(d_noise_var);
+    float* out = static_cast<float*>(d_llr);
+    long long blocks = (n_sym + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    const unsigned g = (unsigned)blocks;
+    if (h->cfg.qam_bits == 2) k_llr_rows<2><<<g, 256, 0, st>>>(y, e, nv, h->K, nd, n_sym, out);
+    else if (h->cfg.qam_bits == 4) k_llr_rows<4><<<g, 256, 0, st>>>(y, e, nv, h->K, nd, n_sym, out);
+    else k_llr_rows<6><<<g, 256, 0, st>>>(y, e, nv, h->K, nd, n_sym, out);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
 }
 
 int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,

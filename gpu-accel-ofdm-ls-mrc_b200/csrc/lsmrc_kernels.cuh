@@ -1075,4 +1075,98 @@ __global__ void k_sync_assemble(const float2* __restrict__ buf1, const float2* _
     }
 }
 
+// ---- soft-output helpers on the receiver's outputs (nothing in the reference) ------------
+
+// nearest constellation level of one axis, same comparisons as demap_symbol()
+template <int B>
+__device__ __forceinline__ float slice_axis(float u)
+{
+    const float au = fabsf(u);
+    float lev;
+    if (B == 2) {
+        lev = (float)0.7071067811865476;
+    } else if (B == 4) {
+        const float a = (float)0.31622776601683794;
+        lev = (au > (float)0.6324555320336759) ? 3.0f * a : a;
+    } else {
+        const float a = (float)0.1543033499620919;
+        const float t4 = (float)0.6172133998483676, t2 = (float)0.3086066999241838;
+        const bool outer = au > t4, far = fabsf(__fsub_rn(au, t4)) > t2;
+        lev = outer ? (far ? 7.0f * a : 5.0f * a) : (far ? a : 3.0f * a);
+    }
+    return u < 0.0f ? -lev : lev;
+}
+
+// Decision-directed noise estimate, step 1: CTA (row) sums  E[bin(i)] * |y_i - slice(y_i)|^2  over the K
+// symbols of one combined row [F*(S-1)][K] (ascending frequency) into part[row].  Fixed reduction
+// order (per-thread strided sums, warp shuffles, then warps in order): deterministic.
+template <int B>
+__device__ __forceinline__ void noise_row(const float2* __restrict__ y, const float* __restrict__ e_bin, int K, float* part_out)
+{
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const float2 v = y[i];
+        const float dr = __fsub_rn(v.x, slice_axis<B>(v.x)), di = __fsub_rn(v.y, slice_axis<B>(v.y));
+        int k = i + (K - 1) / 2;
+        if (k >= K) k -= K;
+        acc += e_bin[k] * (dr * dr + di * di);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    __shared__ float s_w[32];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += s_w[w];
+        *part_out = t;
+    }
+}
+
+__global__ void k_noise_rows(const float2* __restrict__ combined, const float* __restrict__ hsqrd, int K, int rows_per_frame,
+                             int qam_bits, float* __restrict__ part)
+{
+    const long long row = blockIdx.x;
+    const int f = (int)(row / rows_per_frame);
+    const float2* y = combined + row * K;
+    const float* e = hsqrd + (long long)f * K;
+    if (qam_bits == 2) noise_row<2>(y, e, K, part + row);
+    else if (qam_bits == 4) noise_row<4>(y, e, K, part + row);
+    else noise_row<6>(y, e, K, part + row);
+}
+
+// step 2: noise_var[f] = sum_s part[f][s] / (rows_per_frame * K), one warp per frame, fixed order
+__global__ void k_noise_frames(const float* __restrict__ part, int rows_per_frame, int K, int n_frames, float* __restrict__ noise_var)
+{
+    const int f = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (f >= n_frames) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int s = lane; s < rows_per_frame; s += 32) acc += part[(long long)f * rows_per_frame + s];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) noise_var[f] = acc / ((float)rows_per_frame * (float)K);
+}
+
+// LLRs of combined symbols with a per-frame noise variance: llr [F][S-1][K][B], same formula as the
+// data kernel's soft epilogue (soft_symbol) with rho = E[bin(i)] / noise_var[f]
+template <int B>
+__global__ void k_llr_rows(const float2* __restrict__ combined, const float* __restrict__ hsqrd, const float* __restrict__ noise_var,
+                           int K, int rows_per_frame, long long n_sym, float* __restrict__ llr)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_sym; idx += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx / K;
+        const int i = (int)(idx - row * K);
+        const int f = (int)(row / rows_per_frame);
+        int k = i + (K - 1) / 2;
+        if (k >= K) k -= K;
+        const float2 v = combined[idx];
+        const float rho = __fmul_rn(hsqrd[(long long)f * K + k], __frcp_rn(noise_var[f]));
+        float l[B];
+        soft_symbol<B>(v.x, v.y, rho, l);
+#pragma unroll
+        for (int q = 0; q < B; ++q) llr[idx * B + q] = l[q];
+    }
+}
+
 }  // namespace lsmrc

@@ -101,6 +101,18 @@ int lsmrc_demod_frames_device(lsmrc_handle h, const void *d_rx, int n_frames, vo
 int lsmrc_demod_frames_device_soft(lsmrc_handle h, const void *d_rx, int n_frames, void *d_combined,
                                    void *d_bits, void *d_llr, float noise_var);
 
+/* Noise variance when the caller does not know it (second half -- not in the reference):
+ * decision-directed estimate per frame from the receiver's own outputs,
+ *   noise_var[f] = mean over data symbols s, subcarriers i of  sum|H|^2[f][bin(i)] * |y[f][s][i] - slice(y[f][s][i])|^2
+ * (after MRC the symbol error has variance noise_var / sum|H|^2; slice = nearest constellation point).
+ * d_combined [F][S-1][K] and d_hsqrd [F][K] as written by lsmrc_demod_frames_device; d_noise_var [F] float.
+ * lsmrc_llr_from_combined then turns the combined symbols into the same max-log LLRs as
+ * lsmrc_demod_frames_device_soft, scaled per frame by d_noise_var[f] (d_llr [F][S-1][K][b]).
+ * Both touch only the outputs (1/A of the input bytes); deterministic reduction order. */
+int lsmrc_estimate_noise_var(lsmrc_handle h, const void *d_combined, const void *d_hsqrd, int n_frames, void *d_noise_var);
+int lsmrc_llr_from_combined(lsmrc_handle h, const void *d_combined, const void *d_hsqrd, const void *d_noise_var, int n_frames,
+                            void *d_llr);
+
 /* ---- whole frames, host buffers (replaces gpuLS::demodOneFrame gpuLS.cu:475: H2D,
  *      compute, D2H inside).  Frames are cut into chunks of <= max_frames and pipelined
  *      over n_lanes streams so that H2D(i+1), kernels(i) and D2H(i-1) overlap.  Host

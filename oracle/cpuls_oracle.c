@@ -243,6 +243,43 @@ void oracle_soft_demap_row(const oc_complex *sym, const float *hsqrd_bin, int K,
     }
 }
 
+/* nearest constellation level of one axis, from the same comparisons as demap_one() */
+static float slice_axis(float u, int qam_bits)
+{
+    const float au = fabsf(u);
+    float lev;
+    if (qam_bits == 2) {
+        lev = (float)0.7071067811865476;
+    } else if (qam_bits == 4) {
+        const float a = (float)0.31622776601683794;
+        lev = (au > (float)0.6324555320336759) ? 3.0f * a : a;
+    } else {
+        const float a = (float)0.1543033499620919;
+        const float t4 = (float)0.6172133998483676, t2 = (float)0.3086066999241838;
+        const int outer = au > t4, far = fabsf(au - t4) > t2;
+        lev = outer ? (far ? 7.0f * a : 5.0f * a) : (far ? a : 3.0f * a);
+    }
+    return u < 0.0f ? -lev : lev;
+}
+
+/* Decision-directed noise-variance estimate of one frame (new):
+ *   mean over data symbols s and subcarriers i of  sum|H|^2[bin(i)] * |y[s][i] - slice(y[s][i])|^2
+ * (after MRC the symbol error has variance noise_var / sum|H|^2).  combined [n_rows][K] ascending frequency,
+ * hsqrd_bin [K] FFT-bin order.  Accumulated in double: the CUDA kernel's fp32 tree sum is compared to 1e-5. */
+double oracle_noise_var_frame(const oc_complex *combined, const float *hsqrd_bin, int K, int n_rows, int qam_bits)
+{
+    double acc = 0.0;
+    int s, i;
+    for (s = 0; s < n_rows; s++)
+        for (i = 0; i < K; i++) {
+            const oc_complex y = combined[(size_t)s * K + i];
+            const float dr = y.real - slice_axis(y.real, qam_bits), di = y.imag - slice_axis(y.imag, qam_bits);
+            const float e2 = dr * dr + di * di;
+            acc += (double)(hsqrd_bin[(i + (K - 1) / 2) % K] * e2);
+        }
+    return acc / ((double)n_rows * (double)K);
+}
+
 typedef struct {
     const oc_complex *rx;
     const oc_complex *x_bin;

@@ -49,6 +49,9 @@ void oracle_demap_row(const oc_complex *sym, int K, int qam_bits, uint8_t *packe
 /* max-log LLRs of one combined row (new; definition in DESIGN.md): llr [K][b], LLR > 0 <=> bit 0 */
 void oracle_soft_demap_row(const oc_complex *sym, const float *hsqrd_bin, int K, int qam_bits, float noise_var, float *llr);
 
+/* decision-directed noise-variance estimate of one frame (new; definition in DESIGN.md) */
+double oracle_noise_var_frame(const oc_complex *combined, const float *hsqrd_bin, int K, int n_rows, int qam_bits);
+
 /* whole batch: rx [F][S][A][N+C]; hconj [F][A][K]; hsqrd [F][K]; combined
  * [F][S-1][K]; bits [F][S-1][row_bytes].  n_threads >= 1 splits frames. */
 int oracle_demod_frames(const oc_complex *rx, const oc_complex *pilot_asc, int F, int S, int A,

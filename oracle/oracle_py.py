@@ -52,6 +52,8 @@ def _lib(fast: bool = False) -> ctypes.CDLL:
         lib.oracle_soft_demap_row.restype = None
         lib.oracle_soft_demap_row.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                               ctypes.c_void_p]
+        lib.oracle_noise_var_frame.restype = ctypes.c_double
+        lib.oracle_noise_var_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.oracle_sync_correlate.restype = ctypes.c_int
         lib.oracle_sync_correlate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -218,3 +220,12 @@ def soft_demap(combined: np.ndarray, hsqrd: np.ndarray, qam_bits: int, noise_var
             _lib().oracle_soft_demap_row(combined[f, s].ctypes.data, hsqrd[f].ctypes.data, K, qam_bits, noise_var,
                                          out[f, s].ctypes.data)
     return out
+
+
+def noise_var(combined: np.ndarray, hsqrd: np.ndarray, qam_bits: int) -> np.ndarray:
+    """decision-directed noise-variance estimate per frame: combined [F,S-1,K], hsqrd [F,K] -> [F] float64"""
+    combined = np.ascontiguousarray(combined, np.complex64)
+    hsqrd = np.ascontiguousarray(hsqrd, np.float32)
+    F, D, K = combined.shape
+    return np.array([_lib().oracle_noise_var_frame(combined[f].ctypes.data, hsqrd[f].ctypes.data, K, D, qam_bits)
+                     for f in range(F)])

@@ -60,3 +60,47 @@ def test_gpu_llrs_match_oracle(ofdm, oracle, dims):
     hard = np.unpackbits(ref["bits"], axis=-1, bitorder="little")[..., : K * b].reshape(F, S - 1, K, b).astype(bool)
     big = np.abs(want) > 1e-3 * np.abs(want).max()
     assert np.array_equal((got < 0)[big], hard[big])
+
+
+@pytest.mark.parametrize("b,snr_db", [(2, 8.0), (4, 16.0), (6, 24.0)])
+def test_noise_estimate_recovers_the_noise_level(oracle, ofdm, b, snr_db):
+    """decision-directed estimate on synthetic frames: unit-power subcarriers at per-antenna SNR `snr_db` have
+    frequency-domain noise variance ~10^(-snr/10) per bin; the estimate is the EFFECTIVE post-combining noise, which
+    also carries the LS estimation error of H (one unit-modulus pilot: x2 for a unit-power symbol, plus
+    second-order terms that grow at low SNR)"""
+    A, N, C, S, F = 8, 256, 16, 9, 2
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=snr_db, seed=3)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    est = oracle.noise_var(ref["combined"], ref["hsqrd"], b)
+    true = 10.0 ** (-snr_db / 10.0)
+    assert est.shape == (F,)
+    assert np.all(est > 1.5 * true) and np.all(est < 3.2 * true), (est, true)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(4, 64, 16, 6, 2, 5), (8, 1024, 64, 4, 4, 3), (6, 512, 32, 3, 6, 2)])
+def test_gpu_noise_estimate_and_llrs_from_combined(ofdm, oracle, dims):
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db={2: 10.0, 4: 15.0, 6: 20.0}[b], seed=29)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    want_nv = oracle.noise_var(ref["combined"], ref["hsqrd"], b)
+    dev = torch.device("cuda:0")
+    rx = torch.view_as_real(torch.from_numpy(d["rx"]).to(dev)).contiguous()
+    comb = torch.empty((F, S - 1, K, 2), device=dev)
+    hsq = torch.empty((F, K), device=dev)
+    nv = torch.zeros(F, device=dev)
+    llr = torch.full((F, S - 1, K, b), float("nan"), device=dev)
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(d["pilot_asc"])
+        r.demod_frames_device(rx, F, comb, None, None, hsq)
+        r.estimate_noise_var(comb, hsq, F, nv)
+        r.llr_from_combined(comb, hsq, nv, F, llr)
+        r.sync()
+    got_nv = nv.cpu().numpy()
+    assert np.allclose(got_nv, want_nv, rtol=2e-5), (got_nv, want_nv)
+    want = np.stack([oracle.soft_demap(ref["combined"][f:f + 1], ref["hsqrd"][f:f + 1], b, float(np.float32(want_nv[f])))[0]
+                     for f in range(F)])
+    assert_close(llr.cpu().numpy(), want, "LLRs from combined", tol=5e-5)
