@@ -5,7 +5,10 @@
 // with a device-wide sync after every step (ShMemSymBuff_gpu.hpp:386-387, gpuLS.cu:365-401).
 //
 //   stream_main --rows A --cols N --prefix C --syms S --qam b --ring L --frames F [--shm /blah]
-// Writes Output_gpu.dat / Bits_gpu.dat and prints frames/s, antenna-samples/s and H2D GB/s.
+//               [--bits-ring /name [--bits-slots n]]
+// Writes Output_gpu.dat / Bits_gpu.dat and prints frames/s, antenna-samples/s and H2D GB/s.  With
+// --bits-ring the packed bits of every frame also go out on a return ring (ShMemBitsBuff) for a
+// downstream process.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -14,12 +17,14 @@
 #include <string>
 #include <vector>
 
-#include "gpuLS.hpp"
+#include "gpuLS.hpp"  // defines cudaEn before the ring header is seen
+#include "ShMemBitsBuff.hpp"
 
 int main(int argc, char** argv)
 {
     int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, qam = LSMRC_QAM_BITS, ring = 0, frames = 1;
-    std::string shm = shmemID, pilots = fileNameForX;
+    std::string shm = shmemID, pilots = fileNameForX, bits_ring;
+    int bits_slots = 8;
     bool write_out = true;
     for (int i = 1; i < argc; ++i) {
         auto val = [&](const char* name) -> const char* {
@@ -36,6 +41,8 @@ int main(int argc, char** argv)
         else if ((v = val("--frames"))) frames = atoi(v);
         else if ((v = val("--shm"))) shm = v;
         else if ((v = val("--pilots"))) pilots = v;
+        else if ((v = val("--bits-ring"))) bits_ring = v;
+        else if ((v = val("--bits-slots"))) bits_slots = atoi(v);
         else if (std::strcmp(argv[i], "--no-output") == 0) write_out = false;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
@@ -57,6 +64,7 @@ int main(int argc, char** argv)
         out.open("Output_gpu.dat", std::ofstream::binary | std::ofstream::trunc);
         outb.open("Bits_gpu.dat", std::ofstream::binary | std::ofstream::trunc);
     }
+    ShMemBitsBuff* ret = bits_ring.empty() ? nullptr : new ShMemBitsBuff(bits_ring, 1, bits_bytes, bits_slots);
     auto collect = [&](int lane) {
         const void *comb = nullptr, *bits = nullptr;
         if (lsmrc_ring_wait(ls.handle, lane, &comb, &bits, nullptr) < 0) {
@@ -66,6 +74,10 @@ int main(int argc, char** argv)
         if (write_out) {
             out.write(static_cast<const char*>(comb), (std::streamsize)comb_bytes);
             outb.write(static_cast<const char*>(bits), (std::streamsize)bits_bytes);
+        }
+        if (ret && !ret->writeFrame(static_cast<const uint8_t*>(bits))) {
+            fprintf(stderr, "return ring: the reader has gone away\n");
+            exit(1);
         }
     };
     const auto t0 = std::chrono::steady_clock::now();
@@ -97,6 +109,7 @@ int main(int argc, char** argv)
     for (int f = (frames > n_lanes ? frames - n_lanes : 0); f < frames; ++f) collect(f % n_lanes);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const double samples = (double)frames * syms * rows * (cols + cp);
+    delete ret;  // unlinks the name; a reader that is still draining keeps its mapping
     char plan[256] = "";
     lsmrc_describe_plan(ls.handle, plan, sizeof plan);
     printf("{\"frames\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f, \"plan\": \"%s\"}\n",

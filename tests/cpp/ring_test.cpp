@@ -10,6 +10,9 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
+#include "ShMemBitsBuff.hpp"
 #include "ShMemSymBuff.hpp"
 
 static complexF pattern(int sym, int a, int n) { return complexF{(float)(sym * 1000 + a), (float)n}; }
@@ -93,8 +96,27 @@ static int read_foreign(const char* shm, int A, int N, int C, int L, int count)
     return 0;
 }
 
+// writer end of the return ring (ShMemBitsBuff, master): frame i carries bytes (i*131 + j*7) & 255
+static int bits_write(const char* name, long frame_bytes, int slots, int frames)
+{
+    ShMemBitsBuff ring(name, 1, (size_t)frame_bytes, slots);
+    std::vector<uint8_t> buf((size_t)frame_bytes);
+    for (int i = 0; i < frames; ++i) {
+        for (long j = 0; j < frame_bytes; ++j) buf[(size_t)j] = (uint8_t)((i * 131 + j * 7) & 255);
+        if (!ring.writeFrame(buf.data())) {
+            fprintf(stderr, "reader went away at frame %d\n", i);
+            return 1;
+        }
+    }
+    // give the reader time to drain before the segment name disappears with this process
+    for (int spin = 0; spin < 2000 && ring.frameReady(); ++spin) usleep(1000);
+    printf("bits ring wrote %d frames\n", frames);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 6 && std::strcmp(argv[1], "bitswrite") == 0) return bits_write(argv[2], atol(argv[3]), atoi(argv[4]), atoi(argv[5]));
     if (argc >= 3 && std::strcmp(argv[1], "selftest") == 0) return selftest(argv[2]);
     if (argc >= 8 && std::strcmp(argv[1], "read") == 0)
         return read_foreign(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));

@@ -158,3 +158,29 @@ def test_standalone_steps_reproduce_the_chain(ofdm, oracle):
     assert_close(torch.view_as_complex(hconj).cpu().numpy(), ref["hconj"][0], "stage Hconj")
     assert_close(hsq.cpu().numpy(), ref["hsqrd"][0], "stage sum|H|^2")
     assert_close(torch.view_as_complex(out).cpu().numpy(), ref["combined"][0], "stage combined")
+
+
+def test_decoded_bits_travel_back_over_the_return_ring(ofdm, oracle, host_bins, tmp_path):
+    """input ring -> stream_main (GPU) -> return ring (ShMemBitsBuff) -> bits_sink: the downstream process
+    receives exactly the oracle's packed bits, frame by frame"""
+    A, N, C, S, b, F = 4, 64, 16, 16, 2, 9
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=10.0, seed=1239)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    frame_bytes = ref["bits"].shape[1] * ref["bits"].shape[2]
+    name = "/lsmrc_bits_" + uuid.uuid4().hex[:8]
+    out = tmp_path / "Bits_ring.dat"
+    sink = subprocess.Popen([os.path.join(host_bins, "bits_sink"), "--shm", name, "--frame-bytes", str(frame_bytes), "--slots", "4",
+                             "--frames", str(F), "--out", str(out)], stdout=subprocess.PIPE, text=True)
+    try:
+        comb, bits, _ = _run_ring(host_bins, tmp_path, "stream_main", ["--bits-ring", name, "--bits-slots", "4"], d, A, N, C, S, b, F,
+                                  4 * S + 1)
+        sink.wait(timeout=60)
+    finally:
+        if sink.poll() is None:
+            sink.kill()
+        if os.path.exists("/dev/shm" + name):
+            os.unlink("/dev/shm" + name)
+    assert sink.returncode == 0
+    got = np.fromfile(out, np.uint8).reshape(ref["bits"].shape)
+    assert np.array_equal(got, ref["bits"])
+    assert np.array_equal(bits, ref["bits"])

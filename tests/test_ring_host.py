@@ -56,7 +56,7 @@ def test_host_programs_build_without_cuda_headers(ofdm):
     ofdm.load_library()  # make sure the .so the programs link exists
     r = subprocess.run(["make", "-C", HOST, "--no-print-directory"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    for exe in ("gpuLS_main", "ring_feeder", "stream_main", "rx_and_corr_gpu"):
+    for exe in ("gpuLS_main", "ring_feeder", "stream_main", "rx_and_corr_gpu", "latency_main", "bits_sink"):
         assert os.path.exists(os.path.join(HOST, "bin", exe))
     # the facade keeps the reference's names (gpuLS.cuh:72-113, gpuLS_main.cu:104-141)
     text = open(os.path.join(HOST, "gpuLS.hpp")).read()
@@ -68,3 +68,31 @@ def test_host_programs_build_without_cuda_headers(ofdm):
     for name in ("readNextSymbol", "readLastSymbol", "readNextSymbolCUDA", "readLastSymbolCUDA", "writeNextSymbolWithWait",
                  "writeNextSymbolNoWait", "setBuffLen", "printTimes", "storeTimes", "createStream", "destroyStream"):
         assert name in ring, name
+
+
+def test_return_ring_carries_frames_of_bits_between_processes(ring_test_bin, ofdm, tmp_path):
+    """ShMemBitsBuff: writer (master) -> shared memory -> host/bits_sink (slave), more frames than slots"""
+    ofdm.load_library()
+    assert subprocess.run(["make", "-C", HOST, "--no-print-directory", "bin/bits_sink"], capture_output=True).returncode == 0
+    name = "/lsmrc_bits_" + uuid.uuid4().hex[:8]
+    frame_bytes, slots, frames = 3835, 4, 23          # c1-like: 15 rows of 16 bytes would be 240; odd size on purpose
+    out = tmp_path / "bits.dat"
+    # reader first: it creates the zeroed segment and waits for the master to initialise it
+    sink = subprocess.Popen([os.path.join(HOST, "bin", "bits_sink"), "--shm", name, "--frame-bytes", str(frame_bytes),
+                             "--slots", str(slots), "--frames", str(frames), "--out", str(out)], stdout=subprocess.PIPE, text=True)
+    try:
+        time.sleep(0.05)
+        w = subprocess.run([ring_test_bin, "bitswrite", name, str(frame_bytes), str(slots), str(frames)],
+                           capture_output=True, text=True, timeout=60)
+        assert w.returncode == 0, w.stderr
+        sink.wait(timeout=60)
+    finally:
+        if sink.poll() is None:
+            sink.kill()
+        if os.path.exists("/dev/shm" + name):
+            os.unlink("/dev/shm" + name)
+    assert sink.returncode == 0
+    import numpy as np
+    got = np.fromfile(out, np.uint8).reshape(frames, frame_bytes)
+    i, j = np.meshgrid(np.arange(frames), np.arange(frame_bytes), indexing="ij")
+    assert np.array_equal(got, ((i * 131 + j * 7) & 255).astype(np.uint8))
