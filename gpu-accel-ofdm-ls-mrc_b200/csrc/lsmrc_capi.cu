@@ -169,7 +169,8 @@ cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int ma
         const unsigned grid = (unsigned)(groups < 4 * (long long)max_data_ctas ? groups : 4 * (long long)max_data_ctas);
         lsmrc_kernel<PL, MODE_FFT, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else if (mode == MODE_PILOT) {
-        lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<(unsigned)(p.n_frames * p.n_groups), PL::THREADS, PL::SMEM_BYTES, st>>>(p);
+        const unsigned grid = (unsigned)(((p.n_frames + p.frames_per_cta - 1) / p.frames_per_cta) * p.n_groups);
+        lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
         long long items;
         KernelParams q = p;
@@ -519,6 +520,14 @@ int launch_pilot(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, f
     p.hconj = d_hconj;
     p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
     p.n_groups = pilot_groups(h, p.n_frames);
+    // few antennas: pack several frames into one CTA so that its teams are not idle, as long as the
+    // packed grid still fills the GPU
+    p.frames_per_cta = 1;
+    if (p.n_groups == 1) {
+        int fpc = h->ops->teams / h->cfg.n_ant;
+        while (fpc > 1 && (p.n_frames + fpc - 1) / fpc < h->pilot_wave) --fpc;
+        if (fpc > 1) p.frames_per_cta = fpc;
+    }
     p.epart = ch.epart;
     p.counters = ch.counters;
     CK(h, h->ops->launch(MODE_PILOT, p, st, h->max_data_ctas, nullptr, nullptr));

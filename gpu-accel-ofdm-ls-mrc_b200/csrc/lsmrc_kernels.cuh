@@ -85,6 +85,7 @@ struct KernelParams {
     float* hsqrd;
     // pilot kernel only: antenna groups per frame, partial-energy scratch [F][G][N], arrival counters [F]
     int n_groups;
+    int frames_per_cta;  // pilot kernel: frames sharing one CTA (> 1 only with n_groups == 1, few antennas)
     float* epart;
     unsigned int* counters;
     // data kernel only: work-item ticket counter (monotonic across launches on one stream) and its
@@ -138,7 +139,13 @@ struct Plan {
     static constexpr int TW2 = (R3 > 1) ? (R2 - 1) * R3 : 0;
     static constexpr int TWN = TW1 + TW2;
     static constexpr int TILE = P * ROW;   // complex elements per tile
-    static constexpr size_t SMEM_BYTES = sizeof(float2) * (size_t)(TWN + HRING + TEAMS * NBUF * TILE);
+    // Per-team tile block.  Teams narrower than a half-warp share 64-bit shared-memory wavefronts
+    // (16 lanes each): lanes (team j, t) must fall on distinct bank pairs, i.e. j*TEAM_STRIDE + t must
+    // be distinct mod 16, which TEAM_STRIDE = T (mod 16) gives.  (An unpadded block is a multiple
+    // of 16 elements for the small plans: every team of a warp on the same banks, 4- to 8-way conflicts.)
+    static constexpr int TEAM_TILES = NBUF * TILE;
+    static constexpr int TEAM_STRIDE = (T >= 16) ? TEAM_TILES : TEAM_TILES + ((T - TEAM_TILES % 16) + 16) % 16;
+    static constexpr size_t SMEM_BYTES = sizeof(float2) * (size_t)(TWN + HRING + TEAMS * TEAM_STRIDE);
     static_assert(!H_RING_ || TWN % 2 == 0, "ring rows must stay 16-byte aligned");
     static_assert(P * R2 * R3 == N, "plan must factor N");
     static_assert(P >= R2 && P >= R3, "thread must own whole butterflies");
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 
     const int team = threadIdx.x / T;
     const int t = threadIdx.x % T;
-    float2* my_tiles = s_tiles + team * (PL::NBUF * PL::TILE);
+    float2* my_tiles = s_tiles + team * PL::TEAM_STRIDE;
 
     if constexpr (MODE != MODE_ONESHOT) {  // (the one-shot mode issues its first row loads before this copy)
         for (int i = threadIdx.x; i < PL::TWN; i += PL::THREADS) smem[i] = p.twiddles[i];
@@ -516,10 +523,17 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             team_sync<PL>(team);
         }
     } else if constexpr (MODE == MODE_PILOT) {
-        // CTA (f, g): frame f, antenna group g of n_groups; inside the CTA the antennas of the
-        // group are dealt round-robin to the teams
-        const int f = blockIdx.x / p.n_groups;
+        // CTA (c, g): frames [c*fpc, (c+1)*fpc), antenna group g of n_groups.  Each of the fpc frames
+        // gets tpf = TEAMS/fpc teams, which share the antennas of the group round-robin.  fpc > 1
+        // (several frames per CTA, only with n_groups == 1) keeps all teams busy when a frame has
+        // fewer antennas than the CTA has teams.
+        const int fpc = p.frames_per_cta;
+        const int tpf = PL::TEAMS / fpc;
+        const int lf = team / tpf, tj = team % tpf;
+        const int cta_f0 = (blockIdx.x / p.n_groups) * fpc;
         const int g = blockIdx.x % p.n_groups;
+        const bool f_ok = lf < fpc && cta_f0 + lf < p.n_frames;
+        const int f = f_ok ? cta_f0 + lf : p.n_frames - 1;
         const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)p.first_sym * p.sym_stride + p.cp;
         float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
         float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
@@ -534,12 +548,12 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
             xden[sl] = 1.0f / (xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y);
         }
-        const int per_iter = p.n_groups * PL::TEAMS;
+        const int per_iter = p.n_groups * tpf;
         const int n_iter = (p.n_ant + per_iter - 1) / per_iter;
         for (int it = 0; it < n_iter; ++it) {
-            const int a_raw = (it * p.n_groups + g) * PL::TEAMS + team;
-            const bool a_ok = a_raw < p.n_ant;
-            const int a = a_ok ? a_raw : p.n_ant - 1;
+            const int a_raw = (it * p.n_groups + g) * tpf + tj;
+            const bool a_ok = f_ok && a_raw < p.n_ant;
+            const int a = a_raw < p.n_ant ? a_raw : p.n_ant - 1;
             float2* tile = my_tiles + (PL::NBUF == 2 ? (it & 1) * PL::TILE : 0);
             float2* hw_row = hw_frame + (long long)a * N;
             float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
@@ -573,29 +587,33 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             s_e[team * N + bin] = e[sl];
         }
         __syncthreads();
-        float* dst = (p.n_groups == 1) ? (p.hsqrd + (long long)f * K - 1) : (p.epart + ((long long)f * p.n_groups + g) * N);
-        for (int bin = 1 + threadIdx.x; bin < N; bin += PL::THREADS) {
-            float acc = s_e[bin];
-            for (int tm = 1; tm < PL::TEAMS; ++tm) acc += s_e[tm * N + bin];
+        for (int idx = threadIdx.x; idx < fpc * K; idx += PL::THREADS) {
+            const int l2 = idx / K, bin = 1 + idx % K;
+            const int f2 = cta_f0 + l2;
+            if (f2 >= p.n_frames) break;
+            const float* src = s_e + (l2 * tpf) * N + bin;
+            float acc = src[0];
+            for (int tm = 1; tm < tpf; ++tm) acc += src[tm * N];
+            float* dst = (p.n_groups == 1) ? (p.hsqrd + (long long)f2 * K - 1) : (p.epart + ((long long)f2 * p.n_groups + g) * N);
             dst[bin] = acc;
         }
-        if (p.n_groups > 1) {
+        if (p.n_groups > 1) {  // (fpc == 1 here)
             __shared__ unsigned int s_last;
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) {
-                const unsigned int prev = atomicAdd(p.counters + f, 1u);
+                const unsigned int prev = atomicAdd(p.counters + cta_f0, 1u);
                 s_last = (prev == (unsigned)p.n_groups - 1u);
-                if (s_last) p.counters[f] = 0u;  // self-reset for the next launch
+                if (s_last) p.counters[cta_f0] = 0u;  // self-reset for the next launch
             }
             __syncthreads();
             if (s_last) {
                 __threadfence();
-                const float* ep = p.epart + (long long)f * p.n_groups * N;
+                const float* ep = p.epart + (long long)cta_f0 * p.n_groups * N;
                 for (int bin = 1 + threadIdx.x; bin < N; bin += PL::THREADS) {
                     float acc = __ldcg(ep + bin);
                     for (int gg = 1; gg < p.n_groups; ++gg) acc += __ldcg(ep + (long long)gg * N + bin);
-                    p.hsqrd[(long long)f * K + bin - 1] = acc;
+                    p.hsqrd[(long long)cta_f0 * K + bin - 1] = acc;
                 }
             }
         }
@@ -608,7 +626,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         // second launch and the global round trip of H; CTA g == 0 also writes H to global memory
         // for callers that read it back.  The host picks this mode only when the whole batch is
         // one partial wave of CTAs and A*N conj(H) values fit in shared memory.
-        float2* s_h = s_tiles + PL::TEAMS * PL::NBUF * PL::TILE;                 // [A][N]
+        float2* s_h = s_tiles + PL::TEAMS * PL::TEAM_STRIDE;                     // [A][N]
         float* s_esum = reinterpret_cast<float*>(s_h + (size_t)p.n_ant * N);     // [N], entry 0 unused
         const int AS = p.ant_split;           // teams sharing one (frame, symbol)
         const int slots = PL::TEAMS / AS;     // data symbols per CTA
