@@ -251,7 +251,12 @@ PlanOps make_ops()
 #define LSMRC_SMALL_PFH 0
 #endif
 #ifndef LSMRC_SMALL_REGPF
-#define LSMRC_SMALL_REGPF 0
+#define LSMRC_SMALL_REGPF 1
+#endif
+// measured on c1/c5 (16384 frames): 3 CTAs/SM at 168 registers beat 4 at 128 by 15-25 % (the FFT working set no
+// longer spills) and loading the next row into registers behind stage 1 adds another 5-10 %
+#ifndef LSMRC_SMALL_MINB
+#define LSMRC_SMALL_MINB 3
 #endif
 // knobs of the 2048- and 4096-point plans
 #ifndef LSMRC_2048_TEAMS
@@ -295,9 +300,9 @@ PlanOps make_ops()
 const PlanOps* find_plan(int N)
 {
     static const PlanOps plans[] = {
-        make_ops<Plan<64, 16, 4, 1, 32, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, 4>(),
-        make_ops<Plan<128, 16, 8, 1, 16, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, 4>(),
-        make_ops<Plan<256, 16, 16, 1, 8, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, 4>(),
+        make_ops<Plan<64, 16, 4, 1, 32, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
+        make_ops<Plan<128, 16, 8, 1, 16, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
+        make_ops<Plan<256, 16, 16, 1, 8, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<512, 32, 16, 1, 8, 2, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, 0>, 3>(),
         make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>, LSMRC_1024_MINB>(),
         make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>, LSMRC_2048_MINB>(),

@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         }
 
         float2 v[P];
-        if (PL::REG_PF != 0) row_load<PL>(v, x0, t);
+        if (PL::REG_PF != 0) row_load<PL>(v, x0 + (long long)(aj < p.n_ant ? aj : p.n_ant - 1) * p.ant_stride, t);  // this team's first antenna
         const int n_rounds = (p.n_ant + AS - 1) / AS;
         for (int rd = 0; rd < n_rounds; ++rd) {
             // antenna of this round; teams whose slice has run out redo the last antenna and drop the result

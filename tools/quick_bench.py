@@ -14,8 +14,13 @@ ap.add_argument("--config", default="c2")
 ap.add_argument("--frames", type=int, default=64)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--nsym", type=int, default=0)
+ap.add_argument("--dims", default="", help="A,N,C,S,b instead of a named config")
 args = ap.parse_args()
-cfg = m.CONFIGS[args.config]
+if args.dims:
+    A_, N_, C_, S_, b_ = (int(x) for x in args.dims.split(","))
+    cfg = m.RxConfig("custom", A_, N_, C_, S_, b_, 15.0, 1, "custom dims")
+else:
+    cfg = m.CONFIGS[args.config]
 if args.nsym:
     import dataclasses
     cfg = dataclasses.replace(cfg, n_sym=args.nsym)
