@@ -63,6 +63,8 @@ ABI = {
     "lsmrc_sync": (c_int, [c_void_p]),
     "lsmrc_estimate_noise_var": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lsmrc_llr_from_combined": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lsmrc_zf_create": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_int)]),
+    "lsmrc_zf_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lsmrc_set_timing": (c_int, [c_void_p, c_int]),
     "lsmrc_set_oneshot": (c_int, [c_void_p, c_int]),
     "lsmrc_oneshot_count": (ctypes.c_longlong, [c_void_p]),
@@ -190,6 +192,15 @@ class LsMrcReceiver:
 
     def llr_from_combined(self, d_combined, d_hsqrd, d_noise_var, n_frames, d_llr):
         self._ck(self.lib.lsmrc_llr_from_combined(self.h, _ptr(d_combined), _ptr(d_hsqrd), _ptr(d_noise_var), n_frames, _ptr(d_llr)))
+
+    def zf_create(self, d_x, n_ant, n_sc, n_users, d_hzf) -> int:
+        """multi-user zero-forcing matrices (cpuLS.hpp:415-447); returns the number of singular subcarriers"""
+        bad = c_int()
+        self._ck(self.lib.lsmrc_zf_create(self.h, _ptr(d_x), n_ant, n_sc, n_users, _ptr(d_hzf), byref(bad)))
+        return bad.value
+
+    def zf_apply(self, d_hzf, d_xd, n_ant, n_sc, n_users, d_hx):
+        self._ck(self.lib.lsmrc_zf_apply(self.h, _ptr(d_hzf), _ptr(d_xd), n_ant, n_sc, n_users, _ptr(d_hx)))
 
     def demod_frames_host(self, h_rx, n_frames, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
         self._ck(self.lib.lsmrc_demod_frames_host(self.h, _ptr(h_rx), n_frames, _ptr(h_hconj), _ptr(h_hsqrd),

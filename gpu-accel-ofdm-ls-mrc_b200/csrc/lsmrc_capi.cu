@@ -1059,6 +1059,44 @@ int lsmrc_llr_from_combined(lsmrc_handle h, const void* d_combined, const void* 
     return LSMRC_OK;
 }
 
+int lsmrc_zf_create(lsmrc_handle h, const void* d_x, int n_ant, int n_sc, int n_users, void* d_hzf, int* n_singular)
+{
+    if (!h || !d_x || !d_hzf) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_ant < 1 || n_sc < 1 || n_users < 1 || n_users > kZfMaxUsers) return fail(h, LSMRC_ERR_INVALID, "need n_ant, n_sc >= 1 and 1 <= n_users <= 16");
+    if (n_users > n_ant) return fail(h, LSMRC_ERR_INVALID, "more users than antennas: X X^H would be singular");
+    const size_t smem = sizeof(float2) * ((size_t)kZfKT * n_ant * n_users + (size_t)kZfKT * n_users * 2 * n_users);
+    if (smem + 1024 > h->smem_optin) return fail(h, LSMRC_ERR_UNSUPPORTED, "n_ant * n_users too large for one CTA's shared memory");
+    CK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = compute_stream(h);
+    if (!h->d_hit) CK(h, cudaMalloc(&h->d_hit, sizeof(unsigned long long)));
+    int* d_count = reinterpret_cast<int*>(h->d_hit);
+    CK(h, cudaMemsetAsync(d_count, 0, sizeof(int), st));
+    if (smem + 1024 > (48u << 10)) CK(h, cudaFuncSetAttribute(k_zf_create, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_zf_create<<<(unsigned)((n_sc + kZfKT - 1) / kZfKT), 128, smem, st>>>(static_cast<const float2*>(d_x), static_cast<float2*>(d_hzf), n_ant,
+                                                                              n_sc, n_users, d_count);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (n_singular) {
+        CK(h, cudaMemcpyAsync(n_singular, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+    }
+    return LSMRC_OK;
+}
+
+int lsmrc_zf_apply(lsmrc_handle h, const void* d_hzf, const void* d_xd, int n_ant, int n_sc, int n_users, void* d_hx)
+{
+    if (!h || !d_hzf || !d_xd || !d_hx) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (n_ant < 1 || n_sc < 1 || n_users < 1) return fail(h, LSMRC_ERR_INVALID, "bad dimensions");
+    CK(h, cudaSetDevice(h->cfg.device));
+    long long blocks = ((long long)n_ant * n_sc + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_zf_apply<<<(unsigned)blocks, 256, 0, compute_stream(h)>>>(static_cast<const float2*>(d_hzf), static_cast<const float2*>(d_xd),
+                                                               static_cast<float2*>(d_hx), n_ant, n_sc, n_users);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
 int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,
                             void* h_combined, void* h_bits)
 {

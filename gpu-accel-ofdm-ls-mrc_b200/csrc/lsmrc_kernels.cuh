@@ -1187,4 +1187,127 @@ __global__ void k_llr_rows(const float2* __restrict__ combined, const float* __r
     }
 }
 
+// ---- multi-user zero forcing (cpuLS.hpp:400-463, uncalled in the reference) ---------------
+// createZeroForcingMatrix: per subcarrier k, with Xk = X[:, :, k] (U users x A antennas),
+//   Hk = Xk^H * inv(Xk * Xk^H)   (A x U, column-major, ld = A)  ->  Hzf[k][u][a].
+// A CTA takes KT consecutive subcarriers so that the gather from X [U][A][K] reads KT contiguous samples per
+// (user, antenna); Gram matrix, inverse (Gauss-Jordan with partial pivoting, one thread per subcarrier -- U is a
+// handful) and the A x U product all run out of shared memory.  Singular subcarriers (a pivot below 1e-6 of the
+// largest Gram entry) yield a zero block and are counted in *n_singular.
+constexpr int kZfKT = 8;
+constexpr int kZfMaxUsers = 16;
+
+__global__ void k_zf_create(const float2* __restrict__ X, float2* __restrict__ Hzf, int A, int K, int U, int* n_singular)
+{
+    extern __shared__ __align__(16) float2 zsm[];
+    float2* s_x = zsm;                          // [KT][A][U]  (users x antennas, column-major per subcarrier)
+    float2* s_g = s_x + (size_t)kZfKT * A * U;  // [KT][U][2U] augmented rows for the inverse
+    __shared__ int s_ok[kZfKT];
+    const int k0 = blockIdx.x * kZfKT;
+    const int nk = min(kZfKT, K - k0);
+    for (int idx = threadIdx.x; idx < U * A * kZfKT; idx += blockDim.x) {
+        const int kt = idx % kZfKT, ua = idx / kZfKT;  // ua = u*A + a, kt fastest: contiguous in X
+        const int u = ua / A, a = ua - u * A;
+        s_x[((size_t)kt * A + a) * U + u] = (kt < nk) ? X[(size_t)ua * K + k0 + kt] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    // Gram matrix G[u][v] = sum_a x[u,a] * conj(x[v,a]) into the left half of the augmented rows, identity right
+    for (int idx = threadIdx.x; idx < kZfKT * U * U; idx += blockDim.x) {
+        const int kt = idx / (U * U), r = idx % (U * U), u = r / U, v = r % U;
+        const float2* xk = s_x + (size_t)kt * A * U;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int a = 0; a < A; ++a) {
+            const float2 p = xk[a * U + u], q = xk[a * U + v];
+            acc.x += p.x * q.x + p.y * q.y;
+            acc.y += p.y * q.x - p.x * q.y;
+        }
+        float2* row = s_g + ((size_t)kt * U + u) * 2 * U;
+        row[v] = acc;
+        row[U + v] = make_float2(u == v ? 1.f : 0.f, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < kZfKT) {
+        const int kt = threadIdx.x;
+        float2* w = s_g + (size_t)kt * U * 2 * U;
+        bool ok = kt < nk;
+        // a pivot below 1e-6 of the largest Gram entry is rounding noise in fp32: the subcarrier is singular
+        float gmax = 0.f;
+        for (int i = 0; i < U; ++i)
+            for (int j = 0; j < U; ++j) gmax = fmaxf(gmax, fabsf(w[i * 2 * U + j].x) + fabsf(w[i * 2 * U + j].y));
+        const float tiny = 1e-6f * gmax;
+        for (int c = 0; c < U && ok; ++c) {
+            int piv = c;
+            float best = -1.f;
+            for (int i = c; i < U; ++i) {
+                const float m = fabsf(w[i * 2 * U + c].x) + fabsf(w[i * 2 * U + c].y);
+                if (m > best) {
+                    best = m;
+                    piv = i;
+                }
+            }
+            if (!(best > tiny)) {
+                ok = false;
+                break;
+            }
+            if (piv != c)
+                for (int j = 0; j < 2 * U; ++j) {
+                    const float2 tmp = w[c * 2 * U + j];
+                    w[c * 2 * U + j] = w[piv * 2 * U + j];
+                    w[piv * 2 * U + j] = tmp;
+                }
+            const float2 pv = w[c * 2 * U + c];
+            const float den = 1.0f / (pv.x * pv.x + pv.y * pv.y);
+            const float2 pinv = make_float2(pv.x * den, -pv.y * den);
+            for (int j = 0; j < 2 * U; ++j) {
+                const float2 e = w[c * 2 * U + j];
+                w[c * 2 * U + j] = make_float2(e.x * pinv.x - e.y * pinv.y, e.x * pinv.y + e.y * pinv.x);
+            }
+            for (int i = 0; i < U; ++i) {
+                if (i == c) continue;
+                const float2 f = w[i * 2 * U + c];
+                for (int j = 0; j < 2 * U; ++j) {
+                    const float2 e = w[c * 2 * U + j];
+                    w[i * 2 * U + j].x -= f.x * e.x - f.y * e.y;
+                    w[i * 2 * U + j].y -= f.x * e.y + f.y * e.x;
+                }
+            }
+        }
+        s_ok[kt] = ok ? 1 : 0;
+        if (kt < nk && !ok && n_singular) atomicAdd(n_singular, 1);
+    }
+    __syncthreads();
+    // Hk[a][u] = sum_v conj(x[v,a]) * Ginv[v][u]; a fastest so the store is coalesced
+    for (int idx = threadIdx.x; idx < kZfKT * U * A; idx += blockDim.x) {
+        const int kt = idx / (U * A), r = idx % (U * A), u = r / A, a = r % A;
+        if (kt >= nk) continue;
+        const float2* xk = s_x + (size_t)kt * A * U;
+        const float2* gi = s_g + (size_t)kt * U * 2 * U + U;  // right half: row v, column u at gi[v*2U + u]
+        float2 acc = make_float2(0.f, 0.f);
+        if (s_ok[kt]) {
+            for (int v = 0; v < U; ++v) {
+                const float2 p = xk[a * U + v], q = gi[v * 2 * U + u];
+                acc.x += p.x * q.x + p.y * q.y;
+                acc.y += p.x * q.y - p.y * q.x;
+            }
+        }
+        Hzf[(size_t)(k0 + kt) * A * U + (size_t)u * A + a] = acc;
+    }
+}
+
+// multiplyWithChannelInv: HX[a][k] = sum_u Hk[a + A*u] * Xd[u][k]
+__global__ void k_zf_apply(const float2* __restrict__ Hzf, const float2* __restrict__ Xd, float2* __restrict__ HX, int A, int K, int U)
+{
+    const long long n = (long long)A * K;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx / A), a = (int)(idx - (long long)k * A);  // a fastest: coalesced Hzf reads
+        float2 acc = make_float2(0.f, 0.f);
+        for (int u = 0; u < U; ++u) {
+            const float2 h = Hzf[(size_t)k * A * U + (size_t)u * A + a], x = Xd[(size_t)u * K + k];
+            acc.x += h.x * x.x - h.y * x.y;
+            acc.y += h.x * x.y + h.y * x.x;
+        }
+        HX[(size_t)a * K + k] = acc;
+    }
+}
+
 }  // namespace lsmrc

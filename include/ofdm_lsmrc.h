@@ -181,6 +181,17 @@ int lsmrc_sync_correlate(lsmrc_handle h, const void *d_buf, int n_chan, int samp
 int lsmrc_sync_assemble(lsmrc_handle h, const void *d_buf1, const void *d_buf2, int samps, int offset, int pn_len,
                         void *d_rx_frame);
 
+/* ---- multi-user zero forcing (replaces createZeroForcingMatrix cpuLS.hpp:415-447 with rotCube
+ *      :400-413, and multiplyWithChannelInv :449-463 -- defined but never called in the reference; they need
+ *      CBLAS/LAPACK there).  Independent of the handle's receiver dimensions; device pointers, complex64.
+ *      d_x   [n_users][n_ant][n_sc]  per-user channel, the argument createZeroForcingMatrix takes before rotCube
+ *      d_hzf [n_sc][n_users][n_ant]  per subcarrier Hk = Xk^H inv(Xk Xk^H), n_ant x n_users column-major (ld = n_ant)
+ *      n_singular (host, may be NULL): subcarriers whose Gram matrix was singular -- a pivot below 1e-6 of its
+ *      largest entry -- (their block is zero); passing it makes the call synchronous.  n_users <= 16 and <= n_ant.
+ *      lsmrc_zf_apply: d_xd [n_users][n_sc] user symbols -> d_hx [n_ant][n_sc], hx[a][k] = sum_u Hk[a][u] xd[u][k]. */
+int lsmrc_zf_create(lsmrc_handle h, const void *d_x, int n_ant, int n_sc, int n_users, void *d_hzf, int *n_singular);
+int lsmrc_zf_apply(lsmrc_handle h, const void *d_hzf, const void *d_xd, int n_ant, int n_sc, int n_users, void *d_hx);
+
 /* ---- memory and stream plumbing, so callers need no CUDA headers (replaces the raw
  *      cudaMalloc/cudaMemcpy/cudaFree calls of gpuLS_main.cu:73-91,135-139) ------------ */
 int lsmrc_dev_alloc(lsmrc_handle h, size_t bytes, void **d_ptr);

@@ -66,6 +66,10 @@ void oracle_sync_assemble(const oc_complex *buf1, const oc_complex *buf2, int A,
 void oracle_sync_to_slots(const oc_complex *copy_buff, int A, int per_chan, int S, int N, int cp, int keep_cp,
                           oc_complex *slots);
 
+/* multi-user zero-forcing helpers (zf_oracle.c; cpuLS.hpp:400-463): X [U][A][K] -> Hzf [K][U][A]; apply -> HX [A][K] */
+int oracle_zf_create(const oc_complex *X, oc_complex *Hzf, int A, int K, int U);
+void oracle_zf_apply(const oc_complex *Hzf, const oc_complex *Xd, oc_complex *HX, int A, int K, int U);
+
 #ifdef __cplusplus
 }
 #endif

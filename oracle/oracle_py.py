@@ -54,6 +54,10 @@ def _lib(fast: bool = False) -> ctypes.CDLL:
                                               ctypes.c_void_p]
         lib.oracle_noise_var_frame.restype = ctypes.c_double
         lib.oracle_noise_var_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.oracle_zf_create.restype = ctypes.c_int
+        lib.oracle_zf_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.oracle_zf_apply.restype = None
+        lib.oracle_zf_apply.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.oracle_sync_correlate.restype = ctypes.c_int
         lib.oracle_sync_correlate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -229,3 +233,23 @@ def noise_var(combined: np.ndarray, hsqrd: np.ndarray, qam_bits: int) -> np.ndar
     F, D, K = combined.shape
     return np.array([_lib().oracle_noise_var_frame(combined[f].ctypes.data, hsqrd[f].ctypes.data, K, D, qam_bits)
                      for f in range(F)])
+
+
+# ---- multi-user zero forcing (zf_oracle.c; cpuLS.hpp:400-463) --------------------------------------------
+def zf_create(X: np.ndarray):
+    """X [U,A,K] complex64 -> (Hzf [K,U,A] complex64: per subcarrier the A x U matrix, column-major; n_singular)"""
+    X = np.ascontiguousarray(X, np.complex64)
+    U, A, K = X.shape
+    H = np.empty((K, U, A), np.complex64)
+    bad = _lib().oracle_zf_create(X.ctypes.data, H.ctypes.data, A, K, U)
+    return H, bad
+
+
+def zf_apply(Hzf: np.ndarray, Xd: np.ndarray) -> np.ndarray:
+    """Hzf [K,U,A], Xd [U,K] -> HX [A,K]"""
+    Hzf = np.ascontiguousarray(Hzf, np.complex64)
+    Xd = np.ascontiguousarray(Xd, np.complex64)
+    K, U, A = Hzf.shape
+    out = np.empty((A, K), np.complex64)
+    _lib().oracle_zf_apply(Hzf.ctypes.data, Xd.ctypes.data, out.ctypes.data, A, K, U)
+    return out
