@@ -223,8 +223,9 @@ PlanOps make_ops()
 #ifndef LSMRC_1024_NBUF
 #define LSMRC_1024_NBUF 1
 #endif
+// (with X_TMA the rows arrive by bulk copy a third of a row ahead; an extra L2 prefetch costs 4 %)
 #ifndef LSMRC_1024_PFX
-#define LSMRC_1024_PFX 1
+#define LSMRC_1024_PFX 0
 #endif
 #ifndef LSMRC_1024_PFH
 #define LSMRC_1024_PFH 1
@@ -240,6 +241,10 @@ PlanOps make_ops()
 #endif
 #ifndef LSMRC_1024_HRING
 #define LSMRC_1024_HRING true
+#endif
+// antenna rows by bulk async copy into the exchange tile: 2.65 -> 2.48 ms per 256 frames (c2)
+#ifndef LSMRC_1024_XTMA
+#define LSMRC_1024_XTMA true
 #endif
 
 // knobs of the small plans (64..512 points): rows of x prefetched to L2, rows of Hconj prefetched to L1,
@@ -322,7 +327,7 @@ const PlanOps* find_plan(int N)
         make_ops<Plan<128, 16, 8, 1, 16, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<256, 16, 16, 1, 8, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_256_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0>, 3>(),
-        make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>, LSMRC_1024_MINB>(),
+        make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>, LSMRC_1024_MINB>(),
         make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>, LSMRC_2048_MINB>(),
         make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>, LSMRC_4096_MINB>(),
     };
@@ -340,7 +345,7 @@ const OneshotOps* find_oneshot_plan(int N)
         make_oneshot_ops<Plan<128, 8, 4, 4, 16, 1>>(),
         make_oneshot_ops<Plan<256, 8, 8, 4, 8, 1>>(),
         make_oneshot_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0>>(),
-        make_oneshot_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING>>(),
+        make_oneshot_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>>(),
         make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>>(),
         make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>>(),
     };
@@ -565,6 +570,9 @@ int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, fl
     p.hwork = ch.hwork;
     p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
     p.n_groups = 1;
+    // bulk async copies of antenna rows (X_TMA plans) need 16-byte aligned rows: even strides and prefix, aligned base
+    p.x_tma = (reinterpret_cast<uintptr_t>(p.rx) % 16 == 0) && p.cp % 2 == 0 && p.ant_stride % 2 == 0 && p.sym_stride % 2 == 0 &&
+              p.frame_stride % 2 == 0;
     p.ticket = ch.ticket;
     p.ticket_base = ch.ticket_next;
     unsigned grid = 0;

@@ -66,6 +66,7 @@ struct KernelParams {
     // wraps around the end of the shared-memory ring); split_sym >= n_sym when the frame is contiguous
     const float2* rx2;
     int split_sym;
+    int x_tma;      // data kernel, X_TMA plans: antenna rows are 16-byte aligned, bulk copies allowed
     int rx_align4;  // one-launch kernel only: samples are only 4-byte aligned (slots behind the ring's 12-byte header)
     long long frame_stride;
     long long sym_stride;
@@ -108,8 +109,15 @@ struct KernelParams {
     const float2* twiddles;  // plan table: tw1 [(P-1)][T] then tw2 [(R2-1)][R3]
 };
 
-template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false>
+template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false,
+          bool X_TMA_ = false>
 struct Plan {
+    // X_TMA (one warp per row): the data kernel brings each antenna row into the team's tile with one bulk
+    // async copy (TMA), issued while the previous row is still in its last-stage arithmetic, instead of 64-bit
+    // loads into registers at the top of the row.  The copy lays the row out linearly over the first N
+    // elements of the (padded, P x (T+1)) tile; the lanes read their samples from there (conflict-free) and the
+    // tile is then reused in place as the exchange buffer.
+    static constexpr bool X_TMA = X_TMA_;
     // REG_PF: data kernel loads row a+1 into registers while row a is still being processed
     // (0 = off; 1 = all loads right after stage 1; 2 = one load per MRC accumulation, as the
     // register pairs free up).  Only pays with a 255-register budget; off in the shipped plans.
@@ -130,6 +138,10 @@ struct Plan {
     static constexpr int N = N_, P = P_, R2 = R2_, R3 = R3_, TEAMS = TEAMS_, NBUF = NBUF_;
     static constexpr int T = N / P;        // threads per team == M1 (points per row of the tile)
     static constexpr int ROW = T + 1;      // padded tile row (complex elements)
+    // index of element (r, c) of the tile
+    static __device__ __forceinline__ int at(int r, int c) { return r * ROW + c; }
+    static_assert(!X_TMA_ || (R3_ == 1 && N_ / P_ == 32 && NBUF_ == 1 && H_RING_), "X_TMA: one warp per row, two stages, one tile per team, ring plan");
+    static_assert(!X_TMA_ || ((P_ * (N_ / P_ + 1)) % 2 == 0), "X_TMA: team tiles must stay 16-byte aligned");
     static constexpr int NB2 = P / R2;     // stage-2 butterflies per thread
     static constexpr int NB3 = P / R3;     // stage-3 butterflies per thread (R3 > 1)
     static constexpr int RL = (R3 > 1) ? R3 : R2;  // radix of the last stage
@@ -230,6 +242,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <class PL>
 __device__ __forceinline__ void team_sync(int team)
 {
@@ -316,11 +331,17 @@ __device__ __forceinline__ void soft_symbol(float re, float im, float rho, float
 // [0,P) is the thread-local accumulator index and bin = c + (N/RL)*j is the FFT bin.
 // If x_next != nullptr the next row is loaded into `v` as soon as stage 1 has consumed it,
 // so its HBM latency hides behind stage 2/3 and the MRC of this row (register prefetch).
-template <class PL, class Sink>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `after_reads` (two-stage plans) runs once the last-stage operands have been read from the tile, before the
+// last-stage arithmetic: from then on this row no longer needs the tile.
+template <class PL, class Sink, class Hook = NoHook>
 __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __restrict__ x_next,
                                         float2* __restrict__ tile, const float2* __restrict__ s_tw1,
                                         const float2* __restrict__ s_tw2, int t, int team, Sink&& sink,
-                                        const float2* tw_regs = nullptr)
+                                        const float2* tw_regs = nullptr, Hook&& after_reads = Hook())
 {
     constexpr int P = PL::P, T = PL::T, ROW = PL::ROW, R2 = PL::R2, R3 = PL::R3;
     fft_reg<P>(v);
@@ -330,7 +351,7 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
         for (int k1 = 0; k1 < P; ++k1) {
             float2 val = v[brev<P>(k1)];
             if (k1 > 0) val = cmul(val, tw_regs[k1 - 1]);
-            tile[k1 * ROW + t] = val;
+            tile[PL::at(k1, t)] = val;
         }
     } else {
     // Inter-stage twiddles W_N^(t*k1) come from the shared table.  They are fetched in chunks of
@@ -355,7 +376,7 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
             const int k1 = c * TWC + j;
             float2 val = v[brev<P>(k1)];
             if (k1 > 0) val = cmul(val, twa[j]);
-            tile[k1 * ROW + t] = val;
+            tile[PL::at(k1, t)] = val;
         }
         asm volatile("" ::: "memory");
 #pragma unroll
@@ -372,6 +393,9 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
         float2* col = tile + k1 * ROW + m2;
 #pragma unroll
         for (int n2 = 0; n2 < R2; ++n2) u[n2] = col[n2 * R3];
+        if constexpr (R3 == 1) {
+            if (i == PL::NB2 - 1) after_reads();
+        }
         fft_reg<R2>(u);
         if constexpr (R3 == 1) {
 #pragma unroll
@@ -801,6 +825,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         // only refilled two rows after its last use, so the producer practically never waits on a
         // straggling team.
         __shared__ __align__(8) uint64_t bar_full[PL::H_STAGES], bar_empty[PL::H_STAGES];
+        __shared__ __align__(8) uint64_t bar_x[PL::TEAMS];  // X_TMA: one per team, completes on the row's bytes
+        uint32_t x_phase = 0;
         constexpr uint32_t ROW_BYTES = N * sizeof(float2);
         if constexpr (PL::H_RING) {
             if (threadIdx.x == 0) {
@@ -808,6 +834,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                     mbar_init(&bar_full[i], 1);
                     mbar_init(&bar_empty[i], PL::TEAMS);
                 }
+                for (int i = 0; i < PL::TEAMS; ++i) mbar_init(&bar_x[i], 1);
                 mbar_fence_init();
             }
             __syncthreads();
@@ -872,6 +899,14 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 
         float2 v[P];
         if (PL::REG_PF != 0) row_load<PL>(v, x0 + (long long)(aj < p.n_ant ? aj : p.n_ant - 1) * p.ant_stride, t);  // this team's first antenna
+        // X_TMA: row a of this team's symbol arrives in the team's tile by bulk copy; row 0 is requested here,
+        // row a+1 from inside row a (see the hook below).  x_tma is off when rows are not 16-byte aligned.
+        const bool x_tma = PL::X_TMA && p.x_tma;
+        if (PL::X_TMA && x_tma && t == 0) {
+            fence_proxy_async();  // the tile doubled as the previous item's demap byte buffer
+            mbar_expect_tx(&bar_x[team], ROW_BYTES);
+            bulk_g2s(my_tiles, x0, ROW_BYTES, &bar_x[team]);
+        }
         const int n_rounds = (p.n_ant + AS - 1) / AS;
         for (int rd = 0; rd < n_rounds; ++rd) {
             // antenna of this round; teams whose slice has run out redo the last antenna and drop the result
@@ -889,11 +924,20 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             if (PL::REG_PF != 0) {
                 if (a + AS < p.n_ant) x_next = x0 + (long long)(a + AS) * p.ant_stride;
             }
-            if (PL::REG_PF == 0) {
+            if (PL::X_TMA && x_tma) {
+                mbar_wait(&bar_x[team], x_phase);
+                x_phase ^= 1u;
+#pragma unroll
+                for (int n1 = 0; n1 < P; ++n1) v[n1] = tile[n1 * T + t];  // as the copy laid the row out: linear
+                __syncwarp();  // every lane has its samples before stage 1 overwrites the tile
+            } else if (PL::REG_PF == 0) {
                 row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
             }
-            if (PF_X > 0 && a + PF_X * AS < p.n_ant)
-                prefetch_row<T, PL::X_L1>(x0 + (long long)(a + PF_X * AS) * p.ant_stride, N, t);
+            // L2 prefetch: one row ahead of the demand loads, or one row ahead of the next bulk copy
+            // (X_TMA plans whose rows are not 16-byte aligned fall back to demand loads and always prefetch one row)
+            const int pf_rows = (PL::X_TMA && x_tma) ? (PF_X > 0 ? PF_X + 1 : 0) : (PL::X_TMA ? 1 : PF_X);
+            if (pf_rows > 0 && a + pf_rows * AS < p.n_ant)
+                prefetch_row<T, PL::X_L1>(x0 + (long long)(a + pf_rows * AS) * p.ant_stride, N, t);
             if (!PL::H_RING && PF_H > 0 && a + PF_H * AS < p.n_ant)
                 prefetch_row<T, true>(hw_row + (long long)PF_H * AS * N, N, t);
             const int R = rows_done + a;
@@ -919,7 +963,21 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                 if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
-                        PL::TW_REGS ? twr : nullptr);
+                        PL::TW_REGS ? twr : nullptr,
+                        [&]() {
+                            if constexpr (PL::X_TMA) {
+                                // the tile has been read for the last time in this row: fetch the next row
+                                // into it while the last-stage butterflies and the MRC run
+                                if (x_tma && a + 1 < p.n_ant) {
+                                    __syncwarp();
+                                    if (t == 0) {
+                                        fence_proxy_async();
+                                        mbar_expect_tx(&bar_x[team], ROW_BYTES);
+                                        bulk_g2s(tile, x0 + (long long)(a + 1) * p.ant_stride, ROW_BYTES, &bar_x[team]);
+                                    }
+                                }
+                            }
+                        });
             if constexpr (PL::H_RING) {
                 team_sync<PL>(team);
                 if (t == 0) mbar_arrive(&bar_empty[st]);
