@@ -318,6 +318,15 @@ PlanOps make_ops()
 #ifndef LSMRC_4096_MINB
 #define LSMRC_4096_MINB 3
 #endif
+#ifndef LSMRC_512_XTMA
+#define LSMRC_512_XTMA false
+#endif
+#ifndef LSMRC_2048_XTMA
+#define LSMRC_2048_XTMA false
+#endif
+#ifndef LSMRC_4096_XTMA
+#define LSMRC_4096_XTMA false
+#endif
 
 // One plan per FFT size (64..4096).  N/P threads own a row; see lsmrc_kernels.cuh.
 const PlanOps* find_plan(int N)
@@ -326,10 +335,10 @@ const PlanOps* find_plan(int N)
         make_ops<Plan<64, 16, 4, 1, 32, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<128, 16, 8, 1, 16, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<256, 16, 16, 1, 8, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_256_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
-        make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0>, 3>(),
+        make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA>, 3>(),
         make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>, LSMRC_1024_MINB>(),
-        make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>, LSMRC_2048_MINB>(),
-        make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>, LSMRC_4096_MINB>(),
+        make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA>, LSMRC_2048_MINB>(),
+        make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA>, LSMRC_4096_MINB>(),
     };
     for (const PlanOps& o : plans)
         if (o.N == N) return &o;
@@ -344,10 +353,10 @@ const OneshotOps* find_oneshot_plan(int N)
         make_oneshot_ops<Plan<64, 8, 8, 1, 16, 2>>(),
         make_oneshot_ops<Plan<128, 8, 4, 4, 16, 1>>(),
         make_oneshot_ops<Plan<256, 8, 8, 4, 8, 1>>(),
-        make_oneshot_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0>>(),
+        make_oneshot_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA>>(),
         make_oneshot_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>>(),
-        make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING>>(),
-        make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING>>(),
+        make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA>>(),
+        make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA>>(),
     };
     for (const OneshotOps& o : plans)
         if (o.N == N) return &o;

@@ -112,7 +112,7 @@ struct KernelParams {
 template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false,
           bool X_TMA_ = false>
 struct Plan {
-    // X_TMA (one warp per row): the data kernel brings each antenna row into the team's tile with one bulk
+    // X_TMA (teams of whole warps): the data kernel brings each antenna row into the team's tile with one bulk
     // async copy (TMA), issued while the previous row is still in its last-stage arithmetic, instead of 64-bit
     // loads into registers at the top of the row.  The copy lays the row out linearly over the first N
     // elements of the (padded, P x (T+1)) tile; the lanes read their samples from there (conflict-free) and the
@@ -140,7 +140,7 @@ struct Plan {
     static constexpr int ROW = T + 1;      // padded tile row (complex elements)
     // index of element (r, c) of the tile
     static __device__ __forceinline__ int at(int r, int c) { return r * ROW + c; }
-    static_assert(!X_TMA_ || (R3_ == 1 && N_ / P_ == 32 && NBUF_ == 1 && H_RING_), "X_TMA: one warp per row, two stages, one tile per team, ring plan");
+    static_assert(!X_TMA_ || (NBUF_ == 1 && N_ / P_ >= 16), "X_TMA: one tile per team, teams of at least half a warp");
     static_assert(!X_TMA_ || ((P_ * (N_ / P_ + 1)) % 2 == 0), "X_TMA: team tiles must stay 16-byte aligned");
     static constexpr int NB2 = P / R2;     // stage-2 butterflies per thread
     static constexpr int NB3 = P / R3;     // stage-3 butterflies per thread (R3 > 1)
@@ -427,7 +427,27 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
             }
         }
     }
-    if constexpr (R3 > 1) {
+    if constexpr (R3 > 1 && PL::X_TMA) {
+        // bulk-copy plans: read ALL last-stage operands first so that the tile is free for the next row's copy
+        // while the R3-point butterflies and the sink (MRC) run
+        team_sync<PL>(team);
+        float2 w[PL::NB3][R3];
+#pragma unroll
+        for (int i = 0; i < PL::NB3; ++i) {
+            const int c = t + T * i;
+            const float2* src = tile + (c % P) * ROW + (c / P) * R3;
+#pragma unroll
+            for (int m2 = 0; m2 < R3; ++m2) w[i][m2] = src[m2];
+        }
+        after_reads();
+#pragma unroll
+        for (int i = 0; i < PL::NB3; ++i) {
+            const int c = t + T * i;
+            fft_reg<R3>(w[i]);
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) sink(i * R3 + k3, c + (PL::N / R3) * k3, w[i][brev<R3>(k3)]);
+        }
+    } else if constexpr (R3 > 1) {
         team_sync<PL>(team);
 #pragma unroll
         for (int i = 0; i < PL::NB3; ++i) {
@@ -834,6 +854,16 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                     mbar_init(&bar_full[i], 1);
                     mbar_init(&bar_empty[i], PL::TEAMS);
                 }
+                if constexpr (PL::X_TMA) {
+                    for (int i = 0; i < PL::TEAMS; ++i) mbar_init(&bar_x[i], 1);
+                }
+
+                mbar_fence_init();
+            }
+            __syncthreads();
+        }
+        if constexpr (PL::X_TMA && !PL::H_RING) {
+            if (threadIdx.x == 0) {
                 for (int i = 0; i < PL::TEAMS; ++i) mbar_init(&bar_x[i], 1);
                 mbar_fence_init();
             }
@@ -901,7 +931,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         if (PL::REG_PF != 0) row_load<PL>(v, x0 + (long long)(aj < p.n_ant ? aj : p.n_ant - 1) * p.ant_stride, t);  // this team's first antenna
         // X_TMA: row a of this team's symbol arrives in the team's tile by bulk copy; row 0 is requested here,
         // row a+1 from inside row a (see the hook below).  x_tma is off when rows are not 16-byte aligned.
-        const bool x_tma = PL::X_TMA && p.x_tma;
+        const bool x_tma = PL::X_TMA && p.x_tma && AS == 1;  // (with the antenna split rows are not consecutive)
         if (PL::X_TMA && x_tma && t == 0) {
             fence_proxy_async();  // the tile doubled as the previous item's demap byte buffer
             mbar_expect_tx(&bar_x[team], ROW_BYTES);
@@ -929,7 +959,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                 x_phase ^= 1u;
 #pragma unroll
                 for (int n1 = 0; n1 < P; ++n1) v[n1] = tile[n1 * T + t];  // as the copy laid the row out: linear
-                __syncwarp();  // every lane has its samples before stage 1 overwrites the tile
+                team_sync<PL>(team);  // every lane has its samples before stage 1 overwrites the tile
             } else if (PL::REG_PF == 0) {
                 row_load<PL>(v, x0 + (long long)a * p.ant_stride, t);
             }
@@ -969,7 +999,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                 // the tile has been read for the last time in this row: fetch the next row
                                 // into it while the last-stage butterflies and the MRC run
                                 if (x_tma && a + 1 < p.n_ant) {
-                                    __syncwarp();
+                                    team_sync<PL>(team);
                                     if (t == 0) {
                                         fence_proxy_async();
                                         mbar_expect_tx(&bar_x[team], ROW_BYTES);
