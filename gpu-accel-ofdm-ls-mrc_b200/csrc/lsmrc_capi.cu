@@ -6,7 +6,8 @@
 //    buffers once; nothing is allocated, planned or synchronised per symbol
 //    (the reference creates a cuFFT plan and cudaMallocs inside every call and
 //    calls cudaDeviceSynchronize after every launch: gpuLS.cu:377-380,452,471);
-//  * a frame batch costs two launches (pilot, data) regardless of F, S, A;
+//  * a frame batch costs two launches (pilot, data) regardless of F, S, A -- one when it is small enough to be
+//    launch-latency bound (MODE_ONESHOT);
 //  * host-buffer and ring ingest are cut into lanes (stream + staging) so H2D
 //    of the next chunk overlaps the kernels and D2H of the previous ones.
 #include <cuda_runtime.h>
@@ -53,6 +54,9 @@ void fill_twiddles_impl(float2* tw);
 #ifndef LSMRC_ONESHOT
 #define LSMRC_ONESHOT 1
 #endif
+#ifndef LSMRC_ONESHOT_MAX_PILOT_ROUNDS
+#define LSMRC_ONESHOT_MAX_PILOT_ROUNDS 4
+#endif
 constexpr int kOneshotMinb = 1;  // latency mode: one CTA per SM, the full register file
 
 template <class PL>
@@ -62,14 +66,14 @@ size_t oneshot_smem(int n_ant)
 }
 
 // The one-launch mode pays when the call is launch-latency bound: every CTA repeats the channel
-// estimate, so it is used only when that is at most two rounds of row FFTs, the whole batch fits
+// estimate, so it is used only when that is at most LSMRC_ONESHOT_MAX_PILOT_ROUNDS rounds of row FFTs, the whole batch fits
 // in less than one CTA per SM, and conj(H) of a frame fits in shared memory.
 template <class PL>
 int oneshot_split_impl(int n_frames, int n_sym_work, int n_ant, int n_sms, size_t smem_optin)
 {
     if (!LSMRC_ONESHOT || n_sym_work < 1) return 0;
     if (oneshot_smem<PL>(n_ant) > smem_optin) return 0;
-    if ((n_ant + PL::TEAMS - 1) / PL::TEAMS > 2) return 0;
+    if ((n_ant + PL::TEAMS - 1) / PL::TEAMS > LSMRC_ONESHOT_MAX_PILOT_ROUNDS) return 0;
     int as = 1;
     auto ctas = [&](int a) {
         const int slots = PL::TEAMS / a;
@@ -666,6 +670,10 @@ int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frame
     return LSMRC_OK;
 }
 
+// largest batch the one-launch kernel processes in place in pinned host memory (beyond it PCIe bandwidth, not latency,
+// decides and the staged, pipelined path is faster)
+constexpr size_t kZeroCopyBytes = 512u << 10;
+
 // device-visible alias of a pinned (page-locked, mapped) host buffer; nullptr for anything else
 void* mapped_alias(const void* p)
 {
@@ -1129,7 +1137,6 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     // PCIe latency rather than bandwidth decides, is processed in place -- the kernel loads the
     // antenna-samples from and stores the results to the host buffers directly, so the call is one
     // launch and one sync instead of a copy in, the kernels, and up to four copies out.
-    constexpr size_t kZeroCopyBytes = 512u << 10;
     if (h->oneshot && h->zero_copy && h->one_ops && nd > 0 && rx_fb * (size_t)n_frames <= kZeroCopyBytes &&
         h->one_ops->split(n_frames, c.n_sym - 1, c.n_ant, h->n_sms, h->smem_optin) > 0) {
         void* a_rx = mapped_alias(h_rx);
@@ -1295,7 +1302,6 @@ static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L)
 static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_first, const void* h_second, size_t slot_stride_bytes)
 {
     const lsmrc_config& c = h->cfg;
-    constexpr size_t kZeroCopyBytes = 512u << 10;
     if (!(h->oneshot && h->zero_copy && h->one_ops) || c.n_sym < 2 || h->frame_elems * sizeof(float2) > kZeroCopyBytes) return 0;
     if (slot_stride_bytes % sizeof(float2) != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(h_first) | reinterpret_cast<uintptr_t>(h_second)) % sizeof(float) != 0) return 0;

@@ -115,7 +115,7 @@ def test_errors_are_reported(ofdm):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dims", [(16, 64, 16, 16, 2, 1), (4, 64, 16, 16, 2, 2), (24, 64, 16, 5, 6, 1), (16, 128, 32, 9, 4, 1), (32, 128, 32, 3, 2, 2),
+@pytest.mark.parametrize("dims", [(16, 64, 16, 16, 2, 1), (4, 64, 16, 16, 2, 2), (24, 64, 16, 5, 6, 1), (60, 64, 16, 4, 2, 1), (16, 128, 32, 9, 4, 1), (32, 128, 32, 3, 2, 2),
                                   (8, 256, 64, 6, 4, 2), (12, 512, 128, 4, 6, 1), (6, 1024, 64, 5, 4, 1),
                                   (3, 2048, 144, 3, 2, 1), (2, 4096, 288, 3, 6, 1)])
 def test_one_launch_mode_matches_oracle_and_two_kernel_path(ofdm, oracle, dims):
