@@ -325,6 +325,15 @@ PlanOps make_ops()
 #ifndef LSMRC_512_XTMA
 #define LSMRC_512_XTMA false
 #endif
+#ifndef LSMRC_512_TWREC
+#define LSMRC_512_TWREC false
+#endif
+#ifndef LSMRC_2048_TWREC
+#define LSMRC_2048_TWREC false
+#endif
+#ifndef LSMRC_4096_TWREC
+#define LSMRC_4096_TWREC false
+#endif
 #ifndef LSMRC_2048_XTMA
 #define LSMRC_2048_XTMA false
 #endif
@@ -339,10 +348,10 @@ const PlanOps* find_plan(int N)
         make_ops<Plan<64, 16, 4, 1, 32, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<128, 16, 8, 1, 16, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<256, 16, 16, 1, 8, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_256_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
-        make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA>, 3>(),
+        make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA, LSMRC_512_TWREC>, 3>(),
         make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>, LSMRC_1024_MINB>(),
-        make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA>, LSMRC_2048_MINB>(),
-        make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA>, LSMRC_4096_MINB>(),
+        make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA, LSMRC_2048_TWREC>, LSMRC_2048_MINB>(),
+        make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA, LSMRC_4096_TWREC>, LSMRC_4096_MINB>(),
     };
     for (const PlanOps& o : plans)
         if (o.N == N) return &o;
@@ -357,10 +366,10 @@ const OneshotOps* find_oneshot_plan(int N)
         make_oneshot_ops<Plan<64, 8, 8, 1, 16, 2>>(),
         make_oneshot_ops<Plan<128, 8, 4, 4, 16, 1>>(),
         make_oneshot_ops<Plan<256, 8, 8, 4, 8, 1>>(),
-        make_oneshot_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA>>(),
+        make_oneshot_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA, LSMRC_512_TWREC>>(),
         make_oneshot_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>>(),
-        make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA>>(),
-        make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA>>(),
+        make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA, LSMRC_2048_TWREC>>(),
+        make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA, LSMRC_4096_TWREC>>(),
     };
     for (const OneshotOps& o : plans)
         if (o.N == N) return &o;

@@ -110,8 +110,14 @@ struct KernelParams {
 };
 
 template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false,
-          bool X_TMA_ = false>
+          bool X_TMA_ = false, bool TW_REC_ = false>
 struct Plan {
+    // TW_REC (data kernel, P = 32): the inter-stage twiddles W^(t*k1) are not read from the shared-memory table but
+    // generated in registers by the recurrence w(k1+1) = w(k1) * W^t, restarted from exact table values every 8
+    // steps (4 register pairs for the whole kernel, one extra complex multiply per twiddle, <= 7 accumulated
+    // roundings).  Pays where the shared-memory/LSU pipe is the limit (the three-stage plans); neutral for N = 1024.
+    static constexpr bool TW_REC = TW_REC_;
+    static_assert(!TW_REC_ || P_ == 32, "TW_REC is written for 32 points per thread");
     // X_TMA (teams of whole warps): the data kernel brings each antenna row into the team's tile with one bulk
     // async copy (TMA), issued while the previous row is still in its last-stage arithmetic, instead of 64-bit
     // loads into registers at the top of the row.  The copy lays the row out linearly over the first N
@@ -352,6 +358,23 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
             float2 val = v[brev<P>(k1)];
             if (k1 > 0) val = cmul(val, tw_regs[k1 - 1]);
             tile[PL::at(k1, t)] = val;
+        }
+    } else if (PL::TW_REC && tw_regs != nullptr) {
+        // tw_regs[0] = W^t; tw_regs[1..3] = exact W^(8t), W^(16t), W^(24t).  The step is laundered through an empty
+        // asm: the chain depends on kernel-lifetime values only, and left visible the compiler hoists all 31
+        // products out of the row loop and spills them.
+        float2 w1 = tw_regs[0];
+        asm volatile("" : "+f"(w1.x), "+f"(w1.y));
+        float2 w = w1;
+#pragma unroll
+        for (int k1 = 0; k1 < P; ++k1) {
+            float2 val = v[brev<P>(k1)];
+            if (k1 > 0) {
+                val = cmul(val, w);
+                if (k1 + 1 < P) w = ((k1 + 1) % 8 == 0) ? tw_regs[(k1 + 1) / 8] : cmul(w, w1);
+            }
+            tile[PL::at(k1, t)] = val;
+            if (k1 % 4 == 3) asm volatile("" ::: "memory");  // keep the twiddle chain from running ahead of its use
         }
     } else {
     // Inter-stage twiddles W_N^(t*k1) come from the shared table.  They are fetched in chunks of
@@ -886,10 +909,14 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             bulk_g2s(s_hring + sr * N, src_row, ROW_BYTES, &bar_full[sr]);
         };
 
-        float2 twr[PL::TW_REGS ? P - 1 : 1];
+        float2 twr[PL::TW_REGS ? P - 1 : PL::TW_REC ? 4 : 1];
         if constexpr (PL::TW_REGS) {
 #pragma unroll
             for (int k1 = 1; k1 < P; ++k1) twr[k1 - 1] = s_tw1[(k1 - 1) * T + t];
+        } else if constexpr (PL::TW_REC) {
+            twr[0] = s_tw1[t];
+#pragma unroll
+            for (int a = 1; a < 4; ++a) twr[a] = s_tw1[(8 * a - 1) * T + t];
         }
         __shared__ int s_item;
         for (;;) {
@@ -993,7 +1020,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                 if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
-                        PL::TW_REGS ? twr : nullptr,
+                        (PL::TW_REGS || PL::TW_REC) ? twr : nullptr,
                         [&]() {
                             if constexpr (PL::X_TMA) {
                                 // the tile has been read for the last time in this row: fetch the next row
