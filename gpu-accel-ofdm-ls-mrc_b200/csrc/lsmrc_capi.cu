@@ -173,7 +173,9 @@ cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int ma
         const unsigned grid = (unsigned)(groups < 4 * (long long)max_data_ctas ? groups : 4 * (long long)max_data_ctas);
         lsmrc_kernel<PL, MODE_FFT, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else if (mode == MODE_PILOT) {
-        const unsigned grid = (unsigned)(((p.n_frames + p.frames_per_cta - 1) / p.frames_per_cta) * p.n_groups);
+        const long long n_virtual = (long long)((p.n_frames + p.frames_per_cta - 1) / p.frames_per_cta) * p.n_groups;
+        const long long cap = p.pilot_grid_cap > 0 ? p.pilot_grid_cap : n_virtual;
+        const unsigned grid = (unsigned)(n_virtual < cap ? n_virtual : cap);  // CTAs stride over the virtual CTAs
         lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
         long long items;
@@ -328,11 +330,13 @@ PlanOps make_ops()
 #ifndef LSMRC_512_TWREC
 #define LSMRC_512_TWREC false
 #endif
+// three-stage plans are bound by the shared-memory/LSU pipe: generating the stage-1 twiddles in registers
+// instead of loading them is worth +2 % (c3) / +3 % (c4); it costs 10 % at 512 points and nothing at 1024
 #ifndef LSMRC_2048_TWREC
-#define LSMRC_2048_TWREC false
+#define LSMRC_2048_TWREC true
 #endif
 #ifndef LSMRC_4096_TWREC
-#define LSMRC_4096_TWREC false
+#define LSMRC_4096_TWREC true
 #endif
 #ifndef LSMRC_2048_XTMA
 #define LSMRC_2048_XTMA false
@@ -580,6 +584,14 @@ int launch_pilot(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, f
     }
     p.epart = ch.epart;
     p.counters = ch.counters;
+    {
+        // tiny virtual CTAs (a round or two of row FFTs per team: few antennas, small N) amortise the per-CTA setup by
+        // striding one resident wave of CTAs over them; larger ones are left to the hardware scheduler, which
+        // balances them better than a static stride
+        const int tpf = h->ops->teams / p.frames_per_cta;
+        const int rounds = (h->cfg.n_ant + p.n_groups * tpf - 1) / (p.n_groups * tpf);
+        p.pilot_grid_cap = rounds <= 2 ? h->pilot_wave : 0;
+    }
     CK(h, h->ops->launch(MODE_PILOT, p, st, h->max_data_ctas, nullptr, nullptr));
     h->launches++;
     return LSMRC_OK;

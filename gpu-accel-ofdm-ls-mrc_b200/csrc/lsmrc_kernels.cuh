@@ -86,6 +86,7 @@ struct KernelParams {
     float* hsqrd;
     // pilot kernel only: antenna groups per frame, partial-energy scratch [F][G][N], arrival counters [F]
     int n_groups;
+    int pilot_grid_cap;  // pilot launch: largest grid (one resident wave); 0 = one CTA per virtual CTA
     int frames_per_cta;  // pilot kernel: frames sharing one CTA (> 1 only with n_groups == 1, few antennas)
     float* epart;
     unsigned int* counters;
@@ -590,31 +591,35 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             team_sync<PL>(team);
         }
     } else if constexpr (MODE == MODE_PILOT) {
-        // CTA (c, g): frames [c*fpc, (c+1)*fpc), antenna group g of n_groups.  Each of the fpc frames
+        // Virtual CTA (c, g): frames [c*fpc, (c+1)*fpc), antenna group g of n_groups.  Each of the fpc frames
         // gets tpf = TEAMS/fpc teams, which share the antennas of the group round-robin.  fpc > 1
         // (several frames per CTA, only with n_groups == 1) keeps all teams busy when a frame has
-        // fewer antennas than the CTA has teams.
+        // fewer antennas than the CTA has teams.  A CTA strides over the virtual CTAs (grid = at most one
+        // resident wave), so the twiddle copy and the pilot reciprocals below are paid once per CTA.
         const int fpc = p.frames_per_cta;
         const int tpf = PL::TEAMS / fpc;
         const int lf = team / tpf, tj = team % tpf;
-        const int cta_f0 = (blockIdx.x / p.n_groups) * fpc;
-        const int g = blockIdx.x % p.n_groups;
-        const bool f_ok = lf < fpc && cta_f0 + lf < p.n_frames;
-        const int f = f_ok ? cta_f0 + lf : p.n_frames - 1;
-        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)p.first_sym * p.sym_stride + p.cp;
-        float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
-        float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
-        float e[P];
         float2 xp[P];   // pilot value per owned bin
         float xden[P];  // 1/|X|^2, hoisted: cpuLS.hpp:240-241 divides by |X|^2 per element (<= 1 ulp apart)
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
             const int i = sl / PL::RL, j = sl % PL::RL;
             const int bin = t + T * i + (N / PL::RL) * j;
-            e[sl] = 0.f;
             xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
             xden[sl] = 1.0f / (xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y);
         }
+        const int n_virtual = ((p.n_frames + fpc - 1) / fpc) * p.n_groups;
+        for (int vb = blockIdx.x; vb < n_virtual; vb += gridDim.x) {
+        const int cta_f0 = (vb / p.n_groups) * fpc;
+        const int g = vb % p.n_groups;
+        const bool f_ok = lf < fpc && cta_f0 + lf < p.n_frames;
+        const int f = f_ok ? cta_f0 + lf : p.n_frames - 1;
+        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)p.first_sym * p.sym_stride + p.cp;
+        float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+        float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
+        float e[P];
+#pragma unroll
+        for (int sl = 0; sl < P; ++sl) e[sl] = 0.f;
         const int per_iter = p.n_groups * tpf;
         const int n_iter = (p.n_ant + per_iter - 1) / per_iter;
         for (int it = 0; it < n_iter; ++it) {
@@ -684,6 +689,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                 }
             }
         }
+        __syncthreads();  // the partial-energy buffer aliases the tiles of the next virtual CTA
+        }  // virtual CTAs
     } else if constexpr (MODE == MODE_ONESHOT) {
         // Whole frames in ONE launch, for calls that are launch-latency bound (a single small frame,
         // BASELINE config c5): CTA (f, g) first estimates the channel of frame f itself -- all its
