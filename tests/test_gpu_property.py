@@ -1,6 +1,8 @@
 """Property-based GPU parity (hypothesis): random dimension sets through the C ABI against the CPU oracle.
 Covers what the table-driven cases do not enumerate: arbitrary antenna counts, prefix lengths, frame/symbol
 counts that do not divide the teams-per-CTA or the persistent grid, every FFT size and QAM order."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
@@ -16,22 +18,27 @@ SNR = {2: 12.0, 4: 18.0, 6: 24.0}
 def dims(draw):
     N = draw(st.sampled_from([64, 128, 256, 512, 1024, 2048, 4096]))
     big = N >= 1024
-    A = draw(st.integers(2, 6 if big else 20))
+    wide = os.environ.get("LSMRC_HYP_WIDE") == "1"   # occasional deeper sweep: more antennas / frames / symbols
+    A = draw(st.integers(2, (12 if big else 40) if wide else (6 if big else 20)))
     C = draw(st.integers(0, N // 4))
-    S = draw(st.integers(2, 4 if big else 9))
+    S = draw(st.integers(2, (6 if big else 14) if wide else (4 if big else 9)))
     b = draw(st.sampled_from([2, 4, 6]))
-    F = draw(st.integers(1, 2 if big else 6))
+    F = draw(st.integers(1, (4 if big else 48) if wide else (2 if big else 6)))
     return A, N, C, S, b, F
 
 
-@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+# launch policy 2 (default): small batches take the one-launch kernel; 0: always the pilot + data kernel pair
+@pytest.mark.parametrize("policy", [2, 0])
+@settings(max_examples=int(os.environ.get("LSMRC_HYP_EXAMPLES", "30")), deadline=None, suppress_health_check=list(HealthCheck),
+          derandomize=True)
 @given(d=dims(), seed=st.integers(0, 10_000))
-def test_random_dimensions_match_oracle(ofdm, oracle, d, seed):
+def test_random_dimensions_match_oracle(ofdm, oracle, policy, d, seed):
     A, N, C, S, b, F = d
     data = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=SNR[b], seed=seed)
     ref = oracle.demod_frames(data["rx"], data["pilot_asc"], b, C)
     with ofdm.LsMrcReceiver(A, N, C, S, b, max_frames=2, n_lanes=2) as rx:
         rx.set_pilot(data["pilot_asc"])
+        rx.set_oneshot(policy)
         got = rx.demod_numpy(data["rx"])
     # low-diversity cases can have near-zero sum|H|^2 on a subcarrier, where y/h is ill-conditioned for any
     # fp32 implementation: compare the channel always, the combined symbols where the channel is not in a fade
