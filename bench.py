@@ -333,7 +333,7 @@ def frontend_leg(m, dev_index, peak):
             "assemble_frac_of_hbm_peak": 2 * rx.numel() * 4 / (t_asm * 1e-3) / 1e9 / peak}
 
 
-def ring_stream_leg(m, n_frames=192):
+def ring_stream_leg(m, n_frames=192, feeder_threads=None):
     """BASELINE config c3: 14-symbol slots of a 2048-pt / 128-antenna system streamed through the pinned
     shared-memory ring (producer process = host/ring_feeder, consumer = host/stream_main: whole frames DMA'd
     out of the ring on 3 rotating lanes, H2D of frame i+1 overlapping the kernels of frame i)."""
@@ -344,6 +344,8 @@ def ring_stream_leg(m, n_frames=192):
     import numpy as np
 
     cfg = m.CONFIGS["c3"]
+    if feeder_threads is None:
+        feeder_threads = max(1, min(8, (os.cpu_count() or 2) // 2))
     host = os.path.join(ROOT, "gpu-accel-ofdm-ls-mrc_b200", "host")
     if subprocess.run(["make", "-C", host, "--no-print-directory"], capture_output=True).returncode != 0:
         return {"error": "host programs did not build"}
@@ -359,7 +361,7 @@ def ring_stream_leg(m, n_frames=192):
         dims = ["--rows", str(cfg.n_ant), "--cols", str(cfg.fft_size), "--prefix", str(cfg.cp_len), "--syms", str(cfg.n_sym),
                 "--ring", str(ring), "--shm", shm]
         feeder = subprocess.Popen([os.path.join(host, "bin", "ring_feeder"), "--file", os.path.join(d, "rx.bin"), "--frames", str(base),
-                                   "--repeat", str(n_frames // base), "--threads", "4"] + dims)
+                                   "--repeat", str(n_frames // base), "--threads", str(feeder_threads)] + dims)
         try:
             r = subprocess.run([os.path.join(host, "bin", "stream_main"), "--qam", str(cfg.qam_bits), "--frames", str(n_frames),
                                 "--pilots", os.path.join(d, "Pilots.dat"), "--no-output"] + dims,
@@ -374,7 +376,7 @@ def ring_stream_leg(m, n_frames=192):
             return {"error": (r.stdout + r.stderr)[-300:]}
         out = json.loads(r.stdout.strip().splitlines()[-1])
         out["workload"] = (f"c3: {cfg.fft_size}-pt FFT, {cfg.n_ant} antennas, {cfg.n_sym}-symbol slots, ring of {ring} slots "
-                           f"({cfg.rx_bytes_per_frame / 1e6:.1f} MB per frame), one producer process filling slots with 4 threads")
+                           f"({cfg.rx_bytes_per_frame / 1e6:.1f} MB per frame), one producer process filling slots with {feeder_threads} threads")
         out["note"] = ("bounded by the producer's memcpy into the ring, then by PCIe; the consumer overlaps H2D, both "
                        "kernels and D2H on 3 lanes")
         return out
