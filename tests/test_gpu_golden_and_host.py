@@ -184,3 +184,20 @@ def test_decoded_bits_travel_back_over_the_return_ring(ofdm, oracle, host_bins, 
     got = np.fromfile(out, np.uint8).reshape(ref["bits"].shape)
     assert np.array_equal(got, ref["bits"])
     assert np.array_equal(bits, ref["bits"])
+
+
+def test_latency_harness_reports_every_path(host_bins):
+    """host/latency_main (what bench.py's latency leg runs): every path present, the one-launch policy launches one
+    kernel per frame and is not slower than the kernel pair"""
+    import json
+
+    r = subprocess.run([os.path.join(host_bins, "latency_main"), "--launches", "300", "--warmup", "100"], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("device_one_launch", "host_one_launch_in_place", "host_one_launch_staged", "device_two_kernels", "host_two_kernels",
+                "floor_trivial_kernel"):
+        assert d[key]["p50_us"] > 0 and d[key]["p99_us"] >= d[key]["p50_us"], key
+    assert d["device_one_launch"]["kernels_per_frame"] == 1 and d["device_two_kernels"]["kernels_per_frame"] == 2
+    assert d["device_one_launch"]["p50_us"] < d["device_two_kernels"]["p50_us"]
+    assert d["host_one_launch_in_place"]["p50_us"] < d["host_two_kernels"]["p50_us"]
