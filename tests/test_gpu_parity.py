@@ -71,9 +71,10 @@ def test_bits_recover_source_at_high_snr(ofdm):
     assert np.abs(h_est - d["h_true"]).max() / np.abs(d["h_true"]).max() < 2e-2
 
 
-def test_per_symbol_entry_points_match_frame_path(ofdm, oracle):
-    A, N, C, S, b = 4, 64, 16, 16, 2
-    d = ofdm.synth.make_frames(1, A, N, C, S, b, snr_db=10.0, seed=5)
+@pytest.mark.parametrize("dims", [(4, 64, 16, 16, 2), (6, 1024, 64, 5, 4), (5, 1024, 9, 3, 6), (4, 2048, 144, 3, 4), (8, 256, 32, 4, 6)])
+def test_per_symbol_entry_points_match_frame_path(ofdm, oracle, dims):
+    A, N, C, S, b = dims
+    d = ofdm.synth.make_frames(1, A, N, C, S, b, snr_db=SNR[b], seed=5)
     ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
     with ofdm.LsMrcReceiver(A, N, C, S, b) as rx:
         rx.set_pilot(d["pilot_asc"])
