@@ -424,7 +424,9 @@ def main():
     rx_f = torch.view_as_real(rx)
     comb = torch.empty((F, cfg.n_sym - 1, cfg.K, 2), device=dev, dtype=torch.float32)
     bits = torch.empty((F, cfg.n_sym - 1, cfg.bits_row_bytes), device=dev, dtype=torch.uint8)
-    rcv = m.LsMrcReceiver.from_config(cfg, max_frames=max(1, min(Fe, 8)), device=local, n_lanes=3)
+    # host-path chunks of ~450 MB (8 frames of c2): large enough to run the copy engine flat out, three in flight
+    chunk_frames = max(1, min(Fe, int(round(450e6 / cfg.rx_bytes_per_frame)) or 1))
+    rcv = m.LsMrcReceiver.from_config(cfg, max_frames=chunk_frames, device=local, n_lanes=3)
     rcv.set_pilot(pilot_asc)
     stream = torch.cuda.current_stream(dev)
     rcv.set_stream(stream.cuda_stream)
