@@ -331,6 +331,12 @@ PlanOps make_ops()
 #ifndef LSMRC_SMALL_NBUF
 #define LSMRC_SMALL_NBUF 2
 #endif
+#ifndef LSMRC_64_TEAMS
+#define LSMRC_64_TEAMS 32
+#endif
+#ifndef LSMRC_128_TEAMS
+#define LSMRC_128_TEAMS 16
+#endif
 // 256 points: prefetching the next Hconj row into L1 pays (+10 %, 32 antennas x 2048 frames); it does not for 64/128
 #ifndef LSMRC_256_PFH
 #define LSMRC_256_PFH 1
@@ -397,8 +403,8 @@ PlanOps make_ops()
 const PlanOps* find_plan(int N)
 {
     static const PlanOps plans[] = {
-        make_ops<Plan<64, 16, 4, 1, 32, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
-        make_ops<Plan<128, 16, 8, 1, 16, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
+        make_ops<Plan<64, 16, 4, 1, LSMRC_64_TEAMS, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
+        make_ops<Plan<128, 16, 8, 1, LSMRC_128_TEAMS, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<256, 16, 16, 1, 8, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_256_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
         make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA, LSMRC_512_TWREC>, 3>(),
         make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>, LSMRC_1024_MINB>(),
