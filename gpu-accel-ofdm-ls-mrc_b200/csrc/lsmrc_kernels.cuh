@@ -44,9 +44,6 @@
 
 #include "fft_radix.cuh"
 
-#ifndef LSMRC_TW_REGS
-#define LSMRC_TW_REGS 0
-#endif
 #ifndef LSMRC_H_STAGES
 #define LSMRC_H_STAGES 3
 #endif
@@ -125,9 +122,8 @@ struct Plan {
     // elements of the (padded, P x (T+1)) tile; the lanes read their samples from there (conflict-free) and the
     // tile is then reused in place as the exchange buffer.
     static constexpr bool X_TMA = X_TMA_;
-    // REG_PF: data kernel loads row a+1 into registers while row a is still being processed
-    // (0 = off; 1 = all loads right after stage 1; 2 = one load per MRC accumulation, as the
-    // register pairs free up).  Only pays with a 255-register budget; off in the shipped plans.
+    // REG_PF: data kernel loads row a+1 into registers right after stage 1 of row a (0 = off, 1 = on).  Pays for the
+    // 16-points-per-thread plans; the 32-point plans would need a 255-register budget.
     static constexpr int REG_PF = REG_PF_;
     // X_L1: prefetch the antenna-samples into L1 (and load them with L1 allocation) instead of L2
     static constexpr bool X_L1 = X_L1_;
@@ -136,7 +132,6 @@ struct Plan {
     static constexpr bool H_RING = H_RING_;
     static constexpr int H_STAGES = LSMRC_H_STAGES;   // ring depth
     static constexpr int H_AHEAD = LSMRC_H_STAGES - 2; // rows kept in flight ahead of the row being consumed
-    static constexpr bool TW_REGS = LSMRC_TW_REGS != 0 && H_RING_;  // stage-1 twiddles in registers (data kernel)
     static constexpr int TW_CHUNK = (P_ >= 8) ? LSMRC_TW_CHUNK : P_;  // inter-stage twiddles fetched this many at a time
     static constexpr int HRING = H_RING_ ? H_STAGES * N_ : 0;  // complex elements
     // PF_X: rows ahead whose antenna-samples are prefetched into L2; PF_H: rows ahead whose
@@ -352,15 +347,7 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
 {
     constexpr int P = PL::P, T = PL::T, ROW = PL::ROW, R2 = PL::R2, R3 = PL::R3;
     fft_reg<P>(v);
-    if (PL::TW_REGS && tw_regs != nullptr) {
-        // inter-stage twiddles held in registers for the whole kernel (they depend on the lane only)
-#pragma unroll
-        for (int k1 = 0; k1 < P; ++k1) {
-            float2 val = v[brev<P>(k1)];
-            if (k1 > 0) val = cmul(val, tw_regs[k1 - 1]);
-            tile[PL::at(k1, t)] = val;
-        }
-    } else if (PL::TW_REC && tw_regs != nullptr) {
+    if (PL::TW_REC && tw_regs != nullptr) {
         // tw_regs[0] = W^t; tw_regs[1..3] = exact W^(8t), W^(16t), W^(24t).  The step is laundered through an empty
         // asm: the chain depends on kernel-lifetime values only, and left visible the compiler hoists all 31
         // products out of the row loop and spills them.
@@ -916,11 +903,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             bulk_g2s(s_hring + sr * N, src_row, ROW_BYTES, &bar_full[sr]);
         };
 
-        float2 twr[PL::TW_REGS ? P - 1 : PL::TW_REC ? 4 : 1];
-        if constexpr (PL::TW_REGS) {
-#pragma unroll
-            for (int k1 = 1; k1 < P; ++k1) twr[k1 - 1] = s_tw1[(k1 - 1) * T + t];
-        } else if constexpr (PL::TW_REC) {
+        float2 twr[PL::TW_REC ? 4 : 1];
+        if constexpr (PL::TW_REC) {
             twr[0] = s_tw1[t];
 #pragma unroll
             for (int a = 1; a < 4; ++a) twr[a] = s_tw1[(8 * a - 1) * T + t];
@@ -1017,17 +1001,12 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                     h_ready = true;
                                 }
                                 acc[sl] = cmac(acc[sl], h_src[bin], y);
-                                if constexpr (PL::REG_PF == 2) {
-                                    // the register pair that held this row's sample sl is free: refill it
-                                    // with the next row's sample so its latency hides behind the rest of the MRC
-                                    if (x_next != nullptr) v[sl] = ld_stream(x_next + sl * T + t);
-                                }
                             } else {
                                 const float2 h = __ldg(h_src + bin);
                                 if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
-                        (PL::TW_REGS || PL::TW_REC) ? twr : nullptr,
+                        PL::TW_REC ? twr : nullptr,
                         [&]() {
                             if constexpr (PL::X_TMA) {
                                 // the tile has been read for the last time in this row: fetch the next row
