@@ -1488,6 +1488,18 @@ int lsmrc_ring_copy_done(lsmrc_handle h, int lane)
     return LSMRC_OK;
 }
 
+int lsmrc_ring_copy_query(lsmrc_handle h, int lane)
+{
+    if (!h || lane < 0 || lane >= (int)h->lanes.size()) return fail(h, LSMRC_ERR_INVALID, "lane out of range");
+    const cudaError_t e = cudaEventQuery(h->lanes[(size_t)lane].copied);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) {
+        cudaGetLastError();
+        return 0;
+    }
+    return fail_cuda(h, e, "cudaEventQuery");
+}
+
 int lsmrc_ring_wait(lsmrc_handle h, int lane, const void** combined, const void** bits, const void** hconj)
 {
     if (!h || lane < 0 || lane >= (int)h->lanes.size()) return fail(h, LSMRC_ERR_INVALID, "lane out of range");

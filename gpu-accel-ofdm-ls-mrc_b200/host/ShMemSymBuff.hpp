@@ -216,6 +216,17 @@ class ShMemSymBuff {
         *n_first = n_sym < until_end ? n_sym : until_end;
         *second = (*n_first < n_sym) ? slot(0) : nullptr;
     }
+    // The same for a frame that sits `skip` slots behind the read pointer, i.e. behind frames that have been handed
+    // out but not released yet (several frames in flight on the GPU at once).
+    void waitFrameAt(int skip, int n_sym, const complexF** first, int* n_first, const complexF** second)
+    {
+        while (available() < skip + n_sym) relax();
+        const int r = (load(kRead) + skip) % len_;
+        const int until_end = len_ - r;
+        *first = slot(r);
+        *n_first = n_sym < until_end ? n_sym : until_end;
+        *second = (*n_first < n_sym) ? slot(0) : nullptr;
+    }
     bool frameReady(int n_sym) { return available() >= n_sym; }
     void releaseSlots(int n) { release(n); }
     int available()

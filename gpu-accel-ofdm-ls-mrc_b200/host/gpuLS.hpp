@@ -68,7 +68,7 @@ class gpuLS {
 
     // Runtime dimensions.  ring_slots == 0 -> no ring (device / host tensors only).
     gpuLS(int rows, int cols, int cp, int n_sym, int qam_bits, int ring_slots, const std::string& shm_uid,
-          int is_master, int device)
+          int is_master, int device, int n_lanes = 3)
         : rows_(rows), cols_(cols), cp_(cp), n_sym_(n_sym), qam_bits_(qam_bits)
     {
         lsmrc_config c;
@@ -79,7 +79,7 @@ class gpuLS {
         c.qam_bits = qam_bits;
         c.max_frames = 1;
         c.device = device;
-        c.n_lanes = 3;
+        c.n_lanes = n_lanes;
         check(lsmrc_create(&c, &handle), "lsmrc_create");
         bits_.resize(lsmrc_bits_row_bytes(cols, qam_bits) * (size_t)(n_sym > 1 ? n_sym - 1 : 1));
         if (ring_slots > 0) {

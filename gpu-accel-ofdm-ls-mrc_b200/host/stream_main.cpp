@@ -5,7 +5,9 @@
 // with a device-wide sync after every step (ShMemSymBuff_gpu.hpp:386-387, gpuLS.cu:365-401).
 //
 //   stream_main --rows A --cols N --prefix C --syms S --qam b --ring L --frames F [--shm /blah]
-//               [--bits-ring /name [--bits-slots n]]
+//               [--lanes n] [--bits-ring /name [--bits-slots n]]
+// --lanes: frames in flight on the GPU at once (default 3, or 8 for frames below 1 MB, which are launch-latency bound).
+// The ring must hold at least lanes frames + 1 slot (default (lanes+1)*S + 1).
 // Writes Output_gpu.dat / Bits_gpu.dat and prints frames/s, antenna-samples/s and H2D GB/s.  With
 // --bits-ring the packed bits of every frame also go out on a return ring (ShMemBitsBuff) for a
 // downstream process.
@@ -24,7 +26,7 @@ int main(int argc, char** argv)
 {
     int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, qam = LSMRC_QAM_BITS, ring = 0, frames = 1;
     std::string shm = shmemID, pilots = fileNameForX, bits_ring;
-    int bits_slots = 8;
+    int bits_slots = 8, n_lanes = 0;
     bool write_out = true;
     for (int i = 1; i < argc; ++i) {
         auto val = [&](const char* name) -> const char* {
@@ -43,15 +45,21 @@ int main(int argc, char** argv)
         else if ((v = val("--pilots"))) pilots = v;
         else if ((v = val("--bits-ring"))) bits_ring = v;
         else if ((v = val("--bits-slots"))) bits_slots = atoi(v);
+        else if ((v = val("--lanes"))) n_lanes = atoi(v);
         else if (std::strcmp(argv[i], "--no-output") == 0) write_out = false;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
         }
     }
-    const int n_lanes = 3;
+    // default: 3 frames in flight for large frames (copy-bound), 8 for frames below 1 MB (launch-latency bound)
+    if (n_lanes < 1 || n_lanes > 64) n_lanes = ((size_t)syms * rows * (cols + cp) * sizeof(complexF) < (1u << 20)) ? 8 : 3;
     if (ring <= 0) ring = (n_lanes + 1) * syms + 1;
-    gpuLS ls(rows, cols, cp, syms, qam, ring, shm, 0, 0);
+    if (ring < n_lanes * syms + 1) {
+        fprintf(stderr, "the ring (%d slots) must hold %d frames of %d slots plus one\n", ring, n_lanes, syms);
+        return 2;
+    }
+    gpuLS ls(rows, cols, cp, syms, qam, ring, shm, 0, 0, n_lanes);
     if (lsmrc_set_pilot_file(ls.handle, pilots.c_str()) < 0) {
         fprintf(stderr, "pilot: %s\n", lsmrc_last_error(ls.handle));
         return 1;
@@ -81,32 +89,47 @@ int main(int argc, char** argv)
         }
     };
     const auto t0 = std::chrono::steady_clock::now();
-    // slots of frame f may only be released once its H2D copy has finished; do that lazily,
-    // one frame behind, so the copy engine always has the next frame queued
-    int pending_release = -1;
+    // Up to n_lanes frames are in flight.  Two things trail the submissions, both in frame order: the slots of a
+    // frame go back to the producer as soon as the GPU no longer reads them (its H2D copy, or the in-place kernel,
+    // has finished -- polled, so the producer refills while the kernels and D2H of later stages still run), and a
+    // lane's results are collected just before the lane is reused.
+    int unreleased = 0, busy = 0;   // frames [f - unreleased, f) still own their slots; [f - busy, f) not collected
+    auto release_oldest = [&](int f, bool block) -> bool {
+        const int lane = (f - unreleased) % n_lanes;
+        if (block) {
+            if (lsmrc_ring_copy_done(ls.handle, lane) < 0) exit(1);
+        } else if (lsmrc_ring_copy_query(ls.handle, lane) != 1) {
+            return false;
+        }
+        ls.buffPtr->releaseSlots(syms);
+        --unreleased;
+        return true;
+    };
     for (int f = 0; f < frames; ++f) {
         const int lane = f % n_lanes;
-        if (f >= n_lanes) collect(lane);
+        if (busy == n_lanes) {
+            while (unreleased == n_lanes) release_oldest(f, true);  // the lane's events are about to be re-recorded
+            collect(lane);
+            --busy;
+        }
+        while (unreleased > 0 && release_oldest(f, false)) {
+        }
         const complexF *first = nullptr, *second = nullptr;
         int n_first = 0;
-        // frame f sits behind the not-yet-released frame f-1 in the ring
-        while (ls.buffPtr->available() < (pending_release >= 0 ? 2 : 1) * syms) sched_yield();
-        if (pending_release >= 0) {
-            lsmrc_ring_copy_done(ls.handle, pending_release);
-            ls.buffPtr->releaseSlots(syms);
+        while (!ls.buffPtr->frameReady((unreleased + 1) * syms)) {
+            if (unreleased > 0 && release_oldest(f, false)) continue;  // a free slot may be what the producer waits for
+            sched_yield();
         }
-        ls.buffPtr->waitFrame(syms, &first, &n_first, &second);
+        ls.buffPtr->waitFrameAt(unreleased * syms, syms, &first, &n_first, &second);
         if (lsmrc_ring_submit_split(ls.handle, lane, first, n_first, second) < 0) {
             fprintf(stderr, "ring_submit: %s\n", lsmrc_last_error(ls.handle));
             return 1;
         }
-        pending_release = lane;
+        ++unreleased;
+        ++busy;
     }
-    if (pending_release >= 0) {
-        lsmrc_ring_copy_done(ls.handle, pending_release);
-        ls.buffPtr->releaseSlots(syms);
-    }
-    for (int f = (frames > n_lanes ? frames - n_lanes : 0); f < frames; ++f) collect(f % n_lanes);
+    while (unreleased > 0) release_oldest(frames, true);
+    for (int f = frames - busy; f < frames; ++f) collect(f % n_lanes);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const double samples = (double)frames * syms * rows * (cols + cp);
     delete ret;  // unlinks the name; a reader that is still draining keeps its mapping

@@ -144,7 +144,9 @@ int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void *h_first, int n
                             const void *h_second); /* frame wraps around the ring end */
 int lsmrc_ring_wait(lsmrc_handle h, int lane, const void **combined, const void **bits,
                     const void **hconj);
-int lsmrc_ring_copy_done(lsmrc_handle h, int lane); /* blocks until the lane's H2D finished (slots reusable) */
+int lsmrc_ring_copy_done(lsmrc_handle h, int lane);
+/* non-blocking form: 1 when the slots of the frame last submitted to `lane` may be reused, 0 when not yet */
+int lsmrc_ring_copy_query(lsmrc_handle h, int lane); /* blocks until the lane's H2D finished (slots reusable) */
 
 /* ---- stand-alone steps: the individually callable kernel wrappers of gpuLS.cuh:87-99.  The fused
  *      entry points above never go through them; they produce the same intermediate tensors the
