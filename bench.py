@@ -333,7 +333,7 @@ def frontend_leg(m, dev_index, peak):
             "assemble_frac_of_hbm_peak": 2 * rx.numel() * 4 / (t_asm * 1e-3) / 1e9 / peak}
 
 
-def ring_stream_leg(m, n_frames=192, feeder_threads=None, config="c3", lanes=3, note=None):
+def ring_stream_leg(m, n_frames=192, feeder_threads=None, config="c3", lanes=3, note=None, batch=1):
     """BASELINE config c3: 14-symbol slots of a 2048-pt / 128-antenna system streamed through the pinned
     shared-memory ring (producer process = host/ring_feeder, consumer = host/stream_main: whole frames DMA'd
     out of the ring on 3 rotating lanes, H2D of frame i+1 overlapping the kernels of frame i)."""
@@ -357,14 +357,14 @@ def ring_stream_leg(m, n_frames=192, feeder_threads=None, config="c3", lanes=3, 
         rx.tofile(os.path.join(d, "rx.bin"))
         m.synth.make_pilot(cfg.K, cfg.seed).tofile(os.path.join(d, "Pilots.dat"))
         shm = "/lsmrc_" + uuid.uuid4().hex[:8]
-        ring = (lanes + 1) * cfg.n_sym + 1
+        ring = (lanes * batch + 1) * cfg.n_sym + 1
         dims = ["--rows", str(cfg.n_ant), "--cols", str(cfg.fft_size), "--prefix", str(cfg.cp_len), "--syms", str(cfg.n_sym),
                 "--ring", str(ring), "--shm", shm]
         feeder = subprocess.Popen([os.path.join(host, "bin", "ring_feeder"), "--file", os.path.join(d, "rx.bin"), "--frames", str(base),
                                    "--repeat", str(n_frames // base), "--threads", str(feeder_threads)] + dims)
         try:
             r = subprocess.run([os.path.join(host, "bin", "stream_main"), "--qam", str(cfg.qam_bits), "--frames", str(n_frames),
-                                "--pilots", os.path.join(d, "Pilots.dat"), "--no-output", "--lanes", str(lanes)] + dims,
+                                "--pilots", os.path.join(d, "Pilots.dat"), "--no-output", "--lanes", str(lanes), "--batch", str(batch)] + dims,
                                cwd=d, capture_output=True, text=True, timeout=300)
             feeder.wait(timeout=60)
         finally:
@@ -549,9 +549,9 @@ def main():
         frontend = frontend_leg(m, local, peak)
         ring_stream = ring_stream_leg(m)
         # BASELINE config c1 through the ring: tiny frames, read in place by the one-launch kernel, 8 in flight
-        ring_stream["c1"] = ring_stream_leg(m, n_frames=8192, feeder_threads=1, config="c1", lanes=8,
+        ring_stream["c1"] = ring_stream_leg(m, n_frames=32768, feeder_threads=1, config="c1", lanes=4, batch=16,
                                             note="launch-latency bound: one fused kernel per frame reads the ring slots in place "
-                                                 "(ring wrap and 4-byte slot alignment included), 8 frames in flight")
+                                                 "(ring wrap and 4-byte slot alignment included); up to 16 waiting frames per launch, 4 launches in flight")
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

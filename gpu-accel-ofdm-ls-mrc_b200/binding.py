@@ -66,6 +66,7 @@ ABI = {
     "lsmrc_zf_create": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_int)]),
     "lsmrc_zf_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lsmrc_ring_copy_query": (c_int, [c_void_p, c_int]),
+    "lsmrc_ring_submit_frames": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]),
     "lsmrc_set_timing": (c_int, [c_void_p, c_int]),
     "lsmrc_set_oneshot": (c_int, [c_void_p, c_int]),
     "lsmrc_oneshot_count": (ctypes.c_longlong, [c_void_p]),

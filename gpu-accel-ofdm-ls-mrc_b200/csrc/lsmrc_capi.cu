@@ -467,7 +467,7 @@ struct Lane {
     float2* d_hconj = nullptr;  // [max_frames][A][K] (reference layout, only when the caller wants it back)
     float2* d_comb = nullptr;   // [max_frames][S-1][K]
     uint8_t* d_bits = nullptr;  // [max_frames][S-1][row]
-    // pinned single-frame result buffers of the ring path
+    // pinned result buffers of the ring path (max_frames frames)
     float2* h_comb = nullptr;
     uint8_t* h_bits = nullptr;
     float2* h_hconj = nullptr;
@@ -476,6 +476,7 @@ struct Lane {
     uint8_t* a_bits = nullptr;
     float2* a_hconj = nullptr;
     bool busy = false;
+    int ring_frames = 0;  // frames of the submission in flight on this lane
 };
 
 std::mutex g_err_mutex;
@@ -827,9 +828,9 @@ int alloc_lane(lsmrc_ctx* h, Lane& L)
     }
     CK(h, cudaMalloc(&L.d_comb, F * nd * h->K * sizeof(float2)));
     CK(h, cudaMalloc(&L.d_bits, F * nd * h->row_bytes));
-    CK(h, cudaMallocHost(&L.h_comb, nd * h->K * sizeof(float2)));
-    CK(h, cudaMallocHost(&L.h_bits, nd * h->row_bytes));
-    CK(h, cudaMallocHost(&L.h_hconj, (size_t)c.n_ant * h->K * sizeof(float2)));
+    CK(h, cudaMallocHost(&L.h_comb, F * nd * h->K * sizeof(float2)));
+    CK(h, cudaMallocHost(&L.h_bits, F * nd * h->row_bytes));
+    CK(h, cudaMallocHost(&L.h_hconj, F * (size_t)c.n_ant * h->K * sizeof(float2)));
     return LSMRC_OK;
 }
 
@@ -1389,36 +1390,39 @@ int lsmrc_get_channel_device(lsmrc_handle h, void* d_hconj, void* d_hsqrd)
 
 // ---- ring lanes -----------------------------------------------------------------------
 
-static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L)
+static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L, int n_frames)
 {
     const lsmrc_config& c = h->cfg;
     const size_t nd = (size_t)(c.n_sym - 1);
     CK(h, cudaEventRecord(L.copied, L.st));
-    int rc = launch_frames(h, L.st, L.d_rx, 1, L.ch, L.d_hconj, nullptr, L.d_comb, L.d_bits, false);
+    int rc = launch_frames(h, L.st, L.d_rx, n_frames, L.ch, L.d_hconj, nullptr, L.d_comb, L.d_bits, false);
     if (rc != LSMRC_OK) return rc;
     if (nd > 0) {
-        CK(h, cudaMemcpyAsync(L.h_comb, L.d_comb, nd * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
-        CK(h, cudaMemcpyAsync(L.h_bits, L.d_bits, nd * h->row_bytes, cudaMemcpyDeviceToHost, L.st));
+        CK(h, cudaMemcpyAsync(L.h_comb, L.d_comb, n_frames * nd * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
+        CK(h, cudaMemcpyAsync(L.h_bits, L.d_bits, n_frames * nd * h->row_bytes, cudaMemcpyDeviceToHost, L.st));
     }
-    CK(h, cudaMemcpyAsync(L.h_hconj, L.d_hconj, (size_t)c.n_ant * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
+    CK(h, cudaMemcpyAsync(L.h_hconj, L.d_hconj, n_frames * (size_t)c.n_ant * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
     CK(h, cudaEventRecord(L.done, L.st));
     L.busy = true;
+    L.ring_frames = n_frames;
     return LSMRC_OK;
 }
 
 // Small frame in a pinned ring: the one-launch kernel reads the slots where they lie and writes the lane's pinned
 // result buffers directly -- no copy in, no copies out.  Returns 1 when it took the frame, 0 when the staged
 // path has to (pageable ring, large frame, one-launch kernel not applicable), < 0 on error.
-static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_first, const void* h_second, size_t slot_stride_bytes)
+static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_first, const void* h_second, size_t slot_stride_bytes,
+                             int n_frames = 1)
 {
     const lsmrc_config& c = h->cfg;
-    if (!(h->oneshot && h->zero_copy && h->one_ops) || c.n_sym < 2 || h->frame_elems * sizeof(float2) > kZeroCopyBytes) return 0;
+    if (!(h->oneshot && h->zero_copy && h->one_ops) || c.n_sym < 2 || h->frame_elems * sizeof(float2) * n_frames > kZeroCopyBytes) return 0;
+    const int n_slots = n_frames * c.n_sym;
     if (slot_stride_bytes % sizeof(float2) != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(h_first) | reinterpret_cast<uintptr_t>(h_second)) % sizeof(float) != 0) return 0;
-    if (h->one_ops->split(1, c.n_sym - 1, c.n_ant, h->n_sms, h->smem_optin) <= 0) return 0;
+    if (h->one_ops->split(n_frames, c.n_sym - 1, c.n_ant, h->n_sms, h->smem_optin) <= 0) return 0;
     void* a1 = mapped_alias(h_first);
-    void* a2 = (n_first < c.n_sym) ? mapped_alias(h_second) : nullptr;
-    if (!a1 || (n_first < c.n_sym && !a2)) return 0;
+    void* a2 = (n_first < n_slots) ? mapped_alias(h_second) : nullptr;
+    if (!a1 || (n_first < n_slots && !a2)) return 0;
     if (!L.a_comb) {
         L.a_comb = static_cast<float2*>(mapped_alias(L.h_comb));
         L.a_bits = static_cast<uint8_t*>(mapped_alias(L.h_bits));
@@ -1428,14 +1432,15 @@ static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_f
     RxLayout lay;
     lay.dense = false;
     lay.sym_stride = (long long)(slot_stride_bytes / sizeof(float2));
-    lay.rx2 = static_cast<const float2*>(a2);
-    lay.split_sym = n_first;
+    lay.rx2 = a2 ? static_cast<const float2*>(a2) : static_cast<const float2*>(a1);  // (unused when the run does not wrap)
+    lay.split_sym = n_first < n_slots ? n_first : n_slots;
     lay.align4 = ((reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(a2)) % sizeof(float2)) != 0;
-    const int rc = launch_frames(h, L.st, static_cast<const float2*>(a1), 1, L.ch, L.a_hconj, nullptr, L.a_comb, L.a_bits, false, &lay);
+    const int rc = launch_frames(h, L.st, static_cast<const float2*>(a1), n_frames, L.ch, L.a_hconj, nullptr, L.a_comb, L.a_bits, false, &lay);
     if (rc != LSMRC_OK) return rc;
     CK(h, cudaEventRecord(L.copied, L.st));  // the slots are free once the kernel has read them
     CK(h, cudaEventRecord(L.done, L.st));
     L.busy = true;
+    L.ring_frames = n_frames;
     h->zero_copy_calls++;
     return 1;
 }
@@ -1458,27 +1463,33 @@ int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_
         CK(h, cudaMemcpy2DAsync(L.d_rx, slot_bytes, h_slots, slot_stride_bytes, slot_bytes, (size_t)h->cfg.n_sym,
                                 cudaMemcpyHostToDevice, L.st));
     }
-    return ring_enqueue_compute(h, L);
+    return ring_enqueue_compute(h, L, 1);
 }
 
-int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void* h_first, int n_first, const void* h_second)
+int lsmrc_ring_submit_frames(lsmrc_handle h, int lane, const void* h_first, int n_first, const void* h_second, int n_frames)
 {
     if (!h || !h_first) return fail(h, LSMRC_ERR_INVALID, "null argument");
     if (!h->have_pilot) return fail(h, LSMRC_ERR_NO_PILOT, "set the pilot first");
     if (lane < 0 || lane >= h->cfg.n_lanes) return fail(h, LSMRC_ERR_INVALID, "lane out of range");
-    if (n_first < 0 || n_first > h->cfg.n_sym || (n_first < h->cfg.n_sym && !h_second))
-        return fail(h, LSMRC_ERR_INVALID, "bad split");
+    if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, LSMRC_ERR_INVALID, "n_frames must be in 1..max_frames");
+    const int n_slots = n_frames * h->cfg.n_sym;
+    if (n_first < 0 || n_first > n_slots || (n_first < n_slots && !h_second)) return fail(h, LSMRC_ERR_INVALID, "bad split");
     CK(h, cudaSetDevice(h->cfg.device));
     int rc = ensure_lanes(h);
     if (rc != LSMRC_OK) return rc;
     Lane& L = h->lanes[(size_t)lane];
     const size_t slot_bytes = h->slot_elems * sizeof(float2);
-    if (n_first > 0 && (rc = ring_try_in_place(h, L, h_first, n_first, h_second, slot_bytes)) != 0) return rc < 0 ? rc : LSMRC_OK;
+    if (n_first > 0 && (rc = ring_try_in_place(h, L, h_first, n_first, h_second, slot_bytes, n_frames)) != 0) return rc < 0 ? rc : LSMRC_OK;
     if (n_first > 0) CK(h, cudaMemcpyAsync(L.d_rx, h_first, slot_bytes * n_first, cudaMemcpyHostToDevice, L.st));
-    if (n_first < h->cfg.n_sym)
-        CK(h, cudaMemcpyAsync(reinterpret_cast<char*>(L.d_rx) + slot_bytes * n_first, h_second,
-                              slot_bytes * (h->cfg.n_sym - n_first), cudaMemcpyHostToDevice, L.st));
-    return ring_enqueue_compute(h, L);
+    if (n_first < n_slots)
+        CK(h, cudaMemcpyAsync(reinterpret_cast<char*>(L.d_rx) + slot_bytes * n_first, h_second, slot_bytes * (n_slots - n_first),
+                              cudaMemcpyHostToDevice, L.st));
+    return ring_enqueue_compute(h, L, n_frames);
+}
+
+int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void* h_first, int n_first, const void* h_second)
+{
+    return lsmrc_ring_submit_frames(h, lane, h_first, n_first, h_second, 1);
 }
 
 int lsmrc_ring_copy_done(lsmrc_handle h, int lane)

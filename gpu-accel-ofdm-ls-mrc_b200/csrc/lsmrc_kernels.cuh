@@ -59,8 +59,9 @@ struct KernelParams {
     // input: antenna-samples, complex64.  element (f, s, a, n) at
     //   rx + f*frame_stride + s*sym_stride + a*ant_stride + n   (n includes the CP)
     const float2* rx;
-    // one-launch kernel only: symbols >= split_sym of the (single) frame continue at rx2 (a frame that
-    // wraps around the end of the shared-memory ring); split_sym >= n_sym when the frame is contiguous
+    // one-launch kernel only, frames read in place from the shared-memory ring: the frames of the launch are
+    // consecutive ring slots (slot f*S + s); slots >= split_sym continue at rx2 (the run wraps around the end of
+    // the ring).  split_sym = INT_MAX: ordinary addressing through frame_stride.
     const float2* rx2;
     int split_sym;
     int x_tma;      // data kernel, X_TMA plans: antenna rows are 16-byte aligned, bulk copies allowed
@@ -696,13 +697,18 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         const int f = blockIdx.x / groups;
         const int g = blockIdx.x % groups;
         const bool writer = (g == 0);
-        const float2* xf = p.rx + (long long)f * p.frame_stride + p.cp;  // symbol 0 = pilot, data from p.first_sym
         int s = g * slots + team / AS;
         bool valid = s < p.n_sym_work;
         if (!valid) s = p.n_sym_work - 1;
-        const int sd = p.first_sym + s;
-        const float2* xd = (sd < p.split_sym) ? xf + (long long)sd * p.sym_stride
-                                              : p.rx2 + p.cp + (long long)(sd - p.split_sym) * p.sym_stride;
+        // symbol 0 of a frame = pilot, data from p.first_sym
+        const bool ring = p.split_sym != 0x7fffffff;
+        auto sym_ptr = [&](int sym) -> const float2* {
+            if (!ring) return p.rx + (long long)f * p.frame_stride + (long long)sym * p.sym_stride + p.cp;
+            const long long slot = (long long)f * (p.first_sym + p.n_sym_work) + sym;  // ring slot of this symbol
+            return (slot < p.split_sym ? p.rx + slot * p.sym_stride : p.rx2 + (slot - p.split_sym) * p.sym_stride) + p.cp;
+        };
+        const float2* xf = sym_ptr(0);
+        const float2* xd = sym_ptr(p.first_sym + s);
 
         // issue every load the first rounds need before anything waits: pilot row, first data row
         // (registers when they are cheap, L2 otherwise), pilot values, twiddles

@@ -68,7 +68,7 @@ class gpuLS {
 
     // Runtime dimensions.  ring_slots == 0 -> no ring (device / host tensors only).
     gpuLS(int rows, int cols, int cp, int n_sym, int qam_bits, int ring_slots, const std::string& shm_uid,
-          int is_master, int device, int n_lanes = 3)
+          int is_master, int device, int n_lanes = 3, int max_frames = 1)
         : rows_(rows), cols_(cols), cp_(cp), n_sym_(n_sym), qam_bits_(qam_bits)
     {
         lsmrc_config c;
@@ -77,7 +77,7 @@ class gpuLS {
         c.cp_len = cp;
         c.n_sym = n_sym;
         c.qam_bits = qam_bits;
-        c.max_frames = 1;
+        c.max_frames = max_frames;
         c.device = device;
         c.n_lanes = n_lanes;
         check(lsmrc_create(&c, &handle), "lsmrc_create");

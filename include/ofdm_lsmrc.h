@@ -141,7 +141,12 @@ int lsmrc_get_channel_device(lsmrc_handle h, void *d_hconj /* [A][K] */, void *d
  *      the lane's pinned result buffers (valid until the lane is submitted again). ------ */
 int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void *h_slots, size_t slot_stride_bytes);
 int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void *h_first, int n_first,
-                            const void *h_second); /* frame wraps around the ring end */
+                            const void *h_second);
+/* Several consecutive frames of the ring in one submission (n_frames <= max_frames): n_first slots at h_first, the
+ * remaining n_frames*S - n_first at h_second (ring wrap).  Small frames are launch-latency bound; batching the frames
+ * that are already waiting in the ring amortises the launch.  lsmrc_ring_wait then returns n_frames results back to
+ * back in the lane's buffers. */
+int lsmrc_ring_submit_frames(lsmrc_handle h, int lane, const void *h_first, int n_first, const void *h_second, int n_frames); /* frame wraps around the ring end */
 int lsmrc_ring_wait(lsmrc_handle h, int lane, const void **combined, const void **bits,
                     const void **hconj);
 int lsmrc_ring_copy_done(lsmrc_handle h, int lane);
