@@ -190,3 +190,30 @@ def test_small_pinned_frames_are_processed_in_place(ofdm, oracle, dims, how):
     assert_close(got["comb"], ref["combined"], "combined")
     assert np.array_equal(got["bits"], ref["bits"]) or threshold_margin(ref["combined"], b) < 1e-5
     assert_close(out2["combined"], got["comb"], "staged vs in place", tol=2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(16, 1024, 64, 9, 4, 40), (4, 64, 16, 16, 2, 300), (8, 2048, 144, 4, 6, 12)])
+def test_results_are_bit_repeatable(ofdm, dims):
+    """fixed reduction orders everywhere (no float atomics; tickets only decide WHO computes an item): the same
+    input gives bit-identical channel estimates, combined symbols and bits on every call"""
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    dev = torch.device("cuda:0")
+    rx = torch.randn((F, S, A, N + C, 2), device=dev)
+    outs = []
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(ofdm.synth.make_pilot(K, 1))
+        for _ in range(4):
+            comb = torch.empty((F, S - 1, K, 2), device=dev)
+            bits = torch.empty((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+            hc = torch.empty((F, A, K, 2), device=dev)
+            hs = torch.empty((F, K), device=dev)
+            r.demod_frames_device(rx, F, comb, bits, hc, hs)
+            r.sync()
+            outs.append((comb, bits, hc, hs))
+    for o in outs[1:]:
+        for a_, b_ in zip(outs[0], o):
+            assert torch.equal(a_, b_)
