@@ -217,3 +217,36 @@ def test_results_are_bit_repeatable(ofdm, dims):
     for o in outs[1:]:
         for a_, b_ in zip(outs[0], o):
             assert torch.equal(a_, b_)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(9, 1024, 64, 11, 4, 64), (5, 1024, 32, 6, 6, 200), (12, 512, 32, 7, 2, 96), (6, 2048, 144, 5, 4, 40)])
+def test_many_frames_through_the_persistent_kernels(ofdm, oracle, dims):
+    """batches large enough that every persistent CTA takes several work items (ticket loop, Hconj ring and bulk-copy
+    barriers wrap many times), with symbol counts that leave teams idle in the last group of a frame"""
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=SNR[b], seed=77)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    dev = torch.device("cuda:0")
+    rx = torch.view_as_real(torch.from_numpy(d["rx"]).to(dev)).contiguous()
+    comb = torch.zeros((F, S - 1, K, 2), device=dev)
+    bits = torch.zeros((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+    hc = torch.zeros((F, A, K, 2), device=dev)
+    hs = torch.zeros((F, K), device=dev)
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(d["pilot_asc"])
+        r.set_oneshot(0)     # the kernel pair, whatever the batch size
+        for _ in range(2):   # second call: ticket base and barrier phases carry over from the first
+            r.demod_frames_device(rx, F, comb, bits, hc, hs)
+        r.sync()
+        assert r.oneshot_count() == 0
+    assert_close(torch.view_as_complex(hc).cpu().numpy(), ref["hconj"], "Hconj")
+    assert_close(hs.cpu().numpy(), ref["hsqrd"], "sum|H|^2")
+    assert_close(torch.view_as_complex(comb).cpu().numpy(), ref["combined"], "combined")
+    got_bits = bits.cpu().numpy()
+    if not np.array_equal(got_bits, ref["bits"]):
+        n_diff = int(np.unpackbits(got_bits ^ ref["bits"]).sum())
+        pytest.fail(f"{n_diff} demapped bits differ (closest oracle symbol is {threshold_margin(ref['combined'], b):.3e} from a threshold)")
