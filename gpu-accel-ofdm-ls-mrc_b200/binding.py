@@ -157,6 +157,9 @@ class LsMrcReceiver:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):  # buffers handed out by pinned_array()
+                self.lib.lsmrc_host_free(self.h, p)
+            self._pinned = []
             self.lib.lsmrc_destroy(self.h)
             self.h = None
 
@@ -281,9 +284,13 @@ class LsMrcReceiver:
         self._ck(self.lib.lsmrc_host_unregister(self.h, _ptr(arr)))
 
     def pinned_array(self, shape, dtype):
-        """numpy array backed by pinned host memory owned by this handle (freed on close)."""
+        """numpy array backed by pinned host memory owned by this handle: freed by close(), after which the
+        array must not be touched."""
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = self.host_alloc(max(n, 1))
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append(p)
         buf = (ctypes.c_char * max(n, 1)).from_address(p)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 

@@ -453,8 +453,7 @@ struct ChanState {
     float* hsqrd = nullptr;           // [frames][K]
     float* epart = nullptr;           // [frames + kPilotCtaTarget][N]
     unsigned int* counters = nullptr; // [frames], zero between launches
-    unsigned long long* ticket = nullptr;  // data-kernel work-item counter, monotonic
-    unsigned long long ticket_next = 0;    // host mirror: value of *ticket once all enqueued launches have run
+    unsigned long long* ticket = nullptr;  // data-kernel work-item counter + departed-CTA counter, self-resetting
     int frames = 0;
 };
 constexpr int kPilotCtaTarget = 4096;  // upper bound on frames*groups - frames (epart scratch rows)
@@ -602,9 +601,10 @@ int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
     CK(h, cudaMalloc(&c.epart, ((size_t)frames + kPilotCtaTarget) * N * sizeof(float)));
     CK(h, cudaMalloc(&c.counters, (size_t)frames * sizeof(unsigned int)));
     CK(h, cudaMemset(c.counters, 0, (size_t)frames * sizeof(unsigned int)));
-    CK(h, cudaMalloc(&c.ticket, sizeof(unsigned long long)));
-    CK(h, cudaMemset(c.ticket, 0, sizeof(unsigned long long)));
-    c.ticket_next = 0;
+    CK(h, cudaMalloc(&c.ticket, 2 * sizeof(unsigned long long)));
+    CK(h, cudaMemset(c.ticket, 0, 2 * sizeof(unsigned long long)));
+    // the memsets run on the legacy stream, the kernels on non-blocking streams that do not order against it
+    CK(h, cudaDeviceSynchronize());
     c.frames = frames;
     return LSMRC_OK;
 }
@@ -685,12 +685,7 @@ int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, fl
     p.x_tma = (reinterpret_cast<uintptr_t>(p.rx) % 16 == 0) && p.cp % 2 == 0 && p.ant_stride % 2 == 0 && p.sym_stride % 2 == 0 &&
               p.frame_stride % 2 == 0;
     p.ticket = ch.ticket;
-    p.ticket_base = ch.ticket_next;
-    unsigned grid = 0;
-    long long items = 0;
-    CK(h, h->ops->launch(MODE_DATA, p, st, h->max_data_ctas, &grid, &items));
-    // every CTA draws tickets until it sees one past the end: items + grid draws in total
-    ch.ticket_next += (unsigned long long)items + grid;
+    CK(h, h->ops->launch(MODE_DATA, p, st, h->max_data_ctas, nullptr, nullptr));
     h->launches++;
     return LSMRC_OK;
 }
@@ -1032,6 +1027,9 @@ int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
         if ((e = cudaMemcpy(h->d_one_tw, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { fail_cuda(h, e, "cudaMemcpy twiddles"); return bail(LSMRC_ERR_CUDA); }
     }
     if ((e = cudaMalloc(&h->d_pilot_bin, (size_t)h->K * sizeof(float2))) != cudaSuccess) { fail_cuda(h, e, "cudaMalloc pilot"); return bail(LSMRC_ERR_CUDA); }
+    // the table uploads above are pageable-memory copies on the legacy stream (they return once staged); the kernels
+    // run on non-blocking streams that do not order against it
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) { fail_cuda(h, e, "cudaDeviceSynchronize"); return bail(LSMRC_ERR_CUDA); }
     *out = h;
     return LSMRC_OK;
 }
@@ -1079,8 +1077,11 @@ int lsmrc_set_pilot(lsmrc_handle h, const float* pilot_asc, int K)
         xb[(size_t)k] = P[(k + (K + 1) / 2) % K];
         if (xb[(size_t)k].x == 0.f && xb[(size_t)k].y == 0.f) return fail(h, LSMRC_ERR_INVALID, "pilot contains a zero subcarrier");
     }
-    CK(h, cudaStreamSynchronize(h->own_stream));
+    // no kernel of this handle may still be reading the old pilot, and the new one must have landed before the
+    // next launch on any of the handle's (non-blocking) streams
+    CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpy(h->d_pilot_bin, xb.data(), (size_t)K * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(h, cudaDeviceSynchronize());
     h->have_pilot = true;
     return LSMRC_OK;
 }
@@ -1744,8 +1745,11 @@ int lsmrc_host_unregister(lsmrc_handle h, void* h_ptr)
 int lsmrc_set_stream(lsmrc_handle h, void* cuda_stream)
 {
     if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    // the channel state of the device-resident path is shared by consecutive calls: drain the stream it was used on
+    CK(h, cudaStreamSynchronize(compute_stream(h)));
     h->user_stream = static_cast<cudaStream_t>(cuda_stream);
-    h->use_user_stream = true;
+    h->use_user_stream = cuda_stream != nullptr;  // NULL = back to the handle's own stream
     return LSMRC_OK;
 }
 int lsmrc_sync(lsmrc_handle h)

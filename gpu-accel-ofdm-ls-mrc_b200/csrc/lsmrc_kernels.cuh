@@ -88,10 +88,10 @@ struct KernelParams {
     int frames_per_cta;  // pilot kernel: frames sharing one CTA (> 1 only with n_groups == 1, few antennas)
     float* epart;
     unsigned int* counters;
-    // data kernel only: work-item ticket counter (monotonic across launches on one stream) and its
-    // value when this launch starts; a CTA's next item is atomicAdd(ticket) - ticket_base
+    // data kernel only: ticket[0] = work-item counter (a CTA's next item is atomicAdd(&ticket[0], 1)), ticket[1] = CTAs
+    // that have drawn their last ticket.  Both are zero between launches: the last CTA to leave resets them, so a
+    // launch carries no host-side state (safe to replay from a CUDA graph or to move between streams).
     unsigned long long* ticket;
-    unsigned long long ticket_base;
     // data kernel, plans without the Hconj ring: antennas of one (frame, symbol) are split over
     // ant_split teams of the CTA (power of two, <= TEAMS) whose partial sums are added in shared
     // memory -- used when there are too few (frame, symbol) pairs to fill the GPU (latency configs)
@@ -918,8 +918,16 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         __shared__ int s_item;
         for (;;) {
         if (threadIdx.x == 0) {
-            const unsigned long long tk = atomicAdd(p.ticket, 1ULL) - p.ticket_base;
+            const unsigned long long tk = atomicAdd(p.ticket, 1ULL);
             s_item = tk < (unsigned long long)n_items ? (int)tk : -1;
+            if (s_item < 0) {
+                // this CTA is done drawing; the last such CTA re-arms the counters for the next launch
+                __threadfence();
+                if (atomicAdd(p.ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+                    p.ticket[0] = 0ULL;
+                    p.ticket[1] = 0ULL;
+                }
+            }
         }
         __syncthreads();
         const int item = s_item;

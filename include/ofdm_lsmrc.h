@@ -140,18 +140,20 @@ int lsmrc_get_channel_device(lsmrc_handle h, void *d_hconj /* [A][K] */, void *d
  *      returns at once; wait() blocks until that lane is done and hands back pointers to
  *      the lane's pinned result buffers (valid until the lane is submitted again). ------ */
 int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void *h_slots, size_t slot_stride_bytes);
+/* one frame that wraps around the end of the ring: n_first slots at h_first, the other S - n_first at h_second */
 int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void *h_first, int n_first,
                             const void *h_second);
 /* Several consecutive frames of the ring in one submission (n_frames <= max_frames): n_first slots at h_first, the
  * remaining n_frames*S - n_first at h_second (ring wrap).  Small frames are launch-latency bound; batching the frames
  * that are already waiting in the ring amortises the launch.  lsmrc_ring_wait then returns n_frames results back to
  * back in the lane's buffers. */
-int lsmrc_ring_submit_frames(lsmrc_handle h, int lane, const void *h_first, int n_first, const void *h_second, int n_frames); /* frame wraps around the ring end */
+int lsmrc_ring_submit_frames(lsmrc_handle h, int lane, const void *h_first, int n_first, const void *h_second, int n_frames);
 int lsmrc_ring_wait(lsmrc_handle h, int lane, const void **combined, const void **bits,
                     const void **hconj);
+/* blocks until the lane's H2D (or, for frames read in place, the kernel) has finished: its ring slots may be reused */
 int lsmrc_ring_copy_done(lsmrc_handle h, int lane);
 /* non-blocking form: 1 when the slots of the frame last submitted to `lane` may be reused, 0 when not yet */
-int lsmrc_ring_copy_query(lsmrc_handle h, int lane); /* blocks until the lane's H2D finished (slots reusable) */
+int lsmrc_ring_copy_query(lsmrc_handle h, int lane);
 
 /* ---- stand-alone steps: the individually callable kernel wrappers of gpuLS.cuh:87-99.  The fused
  *      entry points above never go through them; they produce the same intermediate tensors the
@@ -209,7 +211,9 @@ int lsmrc_host_alloc(lsmrc_handle h, size_t bytes, void **h_ptr); /* pinned */
 int lsmrc_host_free(lsmrc_handle h, void *h_ptr);
 int lsmrc_host_register(lsmrc_handle h, void *h_ptr, size_t bytes); /* pin an existing mapping (the shm ring) */
 int lsmrc_host_unregister(lsmrc_handle h, void *h_ptr);
-int lsmrc_set_stream(lsmrc_handle h, void *cuda_stream); /* run device-resident calls on a caller stream (NULL = own) */
+/* run device-resident calls on a caller stream (NULL = back to the handle's own stream); drains the stream used so
+ * far.  A handle is not thread-safe: calls on one handle must come from one thread at a time. */
+int lsmrc_set_stream(lsmrc_handle h, void *cuda_stream);
 int lsmrc_sync(lsmrc_handle h);
 /* Launch policy for whole-frame calls.  A batch small enough to be launch-latency bound (a single small frame,
  * BASELINE config c5) runs as ONE fused kernel -- channel estimate and data symbols together, H kept in shared

@@ -27,8 +27,41 @@ CASES = {
 }
 
 
+# Full BASELINE dimensions (configs c2, c3, c4; one frame each).  The input frame is 31-126 MB, so these fixtures hold
+# the generator's seed plus a SHA-256 of the generated samples instead of the samples, the reference's combined
+# symbols, sum|H|^2 and bits in full, and H as a SHA-256 plus a strided sample (H alone is 8.4 MB at c4).
+# name -> (A, N, C, S, qam_bits, seed, snr_db)
+FULL_CASES = {
+    "c2_full_A64_N1024_C64_S101_16qam": (64, 1024, 64, 101, 4, 1236, 15.0),
+    "c3_full_A128_N2048_C144_S14_16qam": (128, 2048, 144, 14, 4, 1237, 15.0),
+    "c4_full_A256_N4096_C288_S14_64qam": (256, 4096, 288, 14, 6, 1238, 20.0),
+}
+HCONJ_SAMPLE_STRIDE = 97
+
+
+def sha256(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+
+def make_full():
+    for name, (A, N, C, S, b, seed, snr) in FULL_CASES.items():
+        d = m.synth.make_frames(1, A, N, C, S, b, snr_db=snr, seed=seed)
+        ref = oracle_py.run_reference(d["rx"], d["pilot_asc"], C)
+        assert ref is not None, "oracle/_ref binary missing for " + name
+        bits = np.stack([np.stack([oracle_py.demap_row(ref["combined"][f, s], b)[0] for s in range(S - 1)]) for f in range(1)])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), rx_seed=np.array(seed), snr_db=np.array(snr),
+                            rx_sha256=np.array(sha256(d["rx"])), pilot_asc=d["pilot_asc"], hsqrd=ref["hsqrd"],
+                            combined=ref["combined"], bits=bits, hconj_sha256=np.array(sha256(ref["hconj"])),
+                            hconj_sample=ref["hconj"].ravel()[::HCONJ_SAMPLE_STRIDE].copy(),
+                            dims=np.array([A, N, C, S, b, 1]))
+        print(name, "ok", os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+
+
 def main():
     oracle_py.build(ref=True)
+    make_full()
     for name, (A, N, C, S, b, F, seed, snr, pil) in CASES.items():
         d = m.synth.make_frames(F, A, N, C, S, b, snr_db=snr, seed=seed)
         K = N - 1

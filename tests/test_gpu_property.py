@@ -44,7 +44,10 @@ def test_random_dimensions_match_oracle(ofdm, oracle, policy, d, seed):
     # fp32 implementation: compare the channel always, the combined symbols where the channel is not in a fade
     assert_close(got["hconj"], ref["hconj"], f"{d} Hconj")
     assert_close(got["hsqrd"], ref["hsqrd"], f"{d} sum|H|^2")
-    ok = ref["hsqrd"] > 1e-2 * np.median(ref["hsqrd"])
+    # hsqrd is indexed by FFT bin (k <-> bin k+1), combined is in ascending frequency: sorted[i] = out[(i + (K-1)/2) mod K]
+    # (cpuLS.hpp:135-149), so the fade mask takes the same roll before it is applied to the combined symbols
+    K = N - 1
+    ok = np.roll(ref["hsqrd"] > 1e-2 * np.median(ref["hsqrd"]), -((K - 1) // 2), axis=-1)
     mask = np.broadcast_to(ok[:, None, :], ref["combined"].shape)
     assert_close(np.where(mask, got["combined"], 0), np.where(mask, ref["combined"], 0), f"{d} combined")
     if not np.array_equal(got["bits"], ref["bits"]):
