@@ -61,12 +61,7 @@ struct PilotOps {
 template <class PL>
 void fill_twiddles_impl(float2* tw);
 
-#ifndef LSMRC_ONESHOT
-#define LSMRC_ONESHOT 1
-#endif
-#ifndef LSMRC_ONESHOT_MAX_PILOT_ROUNDS
-#define LSMRC_ONESHOT_MAX_PILOT_ROUNDS 4
-#endif
+constexpr int kOneshotMaxPilotRounds = 4;
 constexpr int kOneshotMinb = 1;  // latency mode: one CTA per SM, the full register file
 
 template <class PL>
@@ -76,14 +71,14 @@ size_t oneshot_smem(int n_ant)
 }
 
 // The one-launch mode pays when the call is launch-latency bound: every CTA repeats the channel
-// estimate, so it is used only when that is at most LSMRC_ONESHOT_MAX_PILOT_ROUNDS rounds of row FFTs, the whole batch fits
+// estimate, so it is used only when that is at most kOneshotMaxPilotRounds rounds of row FFTs, the whole batch fits
 // in less than one CTA per SM, and conj(H) of a frame fits in shared memory.
 template <class PL>
 int oneshot_split_impl(int n_frames, int n_sym_work, int n_ant, int n_sms, size_t smem_optin)
 {
-    if (!LSMRC_ONESHOT || n_sym_work < 1) return 0;
+    if (n_sym_work < 1) return 0;
     if (oneshot_smem<PL>(n_ant) > smem_optin) return 0;
-    if ((n_ant + PL::TEAMS - 1) / PL::TEAMS > LSMRC_ONESHOT_MAX_PILOT_ROUNDS) return 0;
+    if ((n_ant + PL::TEAMS - 1) / PL::TEAMS > kOneshotMaxPilotRounds) return 0;
     int as = 1;
     auto ctas = [&](int a) {
         const int slots = PL::TEAMS / a;
@@ -135,8 +130,16 @@ void fill_twiddles_impl(float2* tw)
     for (int k1 = 1; k1 < PL::P; ++k1)
         for (int t = 0; t < PL::T; ++t) {
             const double ang = -two_pi * (double)(((long long)t * k1) % PL::N) / (double)PL::N;
-            tw[(k1 - 1) * PL::T + t] = make_float2((float)cos(ang), (float)sin(ang));
+            // shuffle-stage plans fold Plan::stage1_sign(t) into the inter-stage twiddles
+            const double sg = (PL::SH == 2 && (t & 3) == 3) || (PL::SH == 4 && (t & 6) == 6) ? -1.0 : 1.0;
+            tw[(k1 - 1) * PL::T + t] = make_float2((float)(sg * cos(ang)), (float)(sg * sin(ang)));
         }
+    if (PL::SH > 1)  // W_T^(q*k2) at [k2][q], k2 = 0..31 (row 0 is all ones: which lanes need it depends on the lane)
+        for (int k2 = 0; k2 < 32; ++k2)
+            for (int q = 0; q < PL::SH; ++q) {
+                const double ang = -two_pi * (double)((q * k2) % PL::T) / (double)PL::T;
+                tw[PL::TW1 + k2 * PL::SH + q] = make_float2((float)cos(ang), (float)sin(ang));
+            }
     if (PL::R3 > 1)
         for (int k2 = 1; k2 < PL::R2; ++k2)
             for (int m2 = 0; m2 < PL::R3; ++m2) {
@@ -145,16 +148,14 @@ void fill_twiddles_impl(float2* tw)
             }
 }
 
-#ifndef LSMRC_PILOT_PLANS
-#define LSMRC_PILOT_PLANS 1
-#endif
-#ifndef LSMRC_PILOT_WIDE
-#define LSMRC_PILOT_WIDE 1
-#endif
 // the pilot kernel keeps the pilot, 1/|X|^2 and the energy partials of its P bins in registers on
 // top of the FFT working set: give the 32-point plans a 255-register budget there
 template <class PL, int MINB>
-constexpr int pilot_minb() { return (LSMRC_PILOT_WIDE && PL::P >= 32 && MINB > 2) ? 2 : MINB; }
+constexpr int pilot_minb() { return (PL::P >= 32 && MINB > 2) ? 2 : MINB; }
+
+// dynamic shared memory of lsmrc_data_sh: W_T^(q*k2) table, per team one channel row and a tile
+template <class PL>
+constexpr size_t data_sh_smem() { return sizeof(float2) * (size_t)(PL::TW2 + PL::TEAMS * (PL::N + PL::TILE)); }
 
 template <class PL, int MINB>
 cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
@@ -173,6 +174,18 @@ cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(pilot_ctas_per_sm, lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()>,
                                                       PL::THREADS, PL::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    if constexpr (PL::SH > 1) {
+        // shuffle-stage plans: large batches run the dedicated data kernel (the generic one serves the antenna-split
+        // launches of tiny batches); both share the persistent grid size
+        e = cudaFuncSetAttribute(lsmrc_data_sh<PL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)data_sh_smem<PL>());
+        if (e != cudaSuccess) return e;
+        int generic = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&generic, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS, PL::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_data_sh<PL, MINB>, PL::THREADS, data_sh_smem<PL>());
+        if (e == cudaSuccess && generic < *data_ctas_per_sm) *data_ctas_per_sm = generic;
+        return e;
+    }
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS,
                                                          PL::SMEM_BYTES);
 }
@@ -211,6 +224,12 @@ cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int ma
         const unsigned grid = (unsigned)(items < max_data_ctas ? items : max_data_ctas);  // persistent CTAs
         if (grid_out) *grid_out = grid;
         if (items_out) *items_out = items;
+        if constexpr (PL::SH > 1) {
+            if (q.ant_split == 1) {
+                lsmrc_data_sh<PL, MINB><<<grid, PL::THREADS, data_sh_smem<PL>(), st>>>(q);
+                return cudaGetLastError();
+            }
+        }
         lsmrc_kernel<PL, MODE_DATA, MINB><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(q);
     }
     return cudaGetLastError();
@@ -270,162 +289,82 @@ PlanOps make_ops()
     return o;
 }
 
-// tuning knobs of the headline N=1024 plan (overridable at build time for experiments)
-#ifndef LSMRC_1024_TEAMS
-#define LSMRC_1024_TEAMS 4
+// ---- the plans.  Template arguments: N, P (points per thread), R2, R3, teams per CTA, tile buffers per team, rows of
+// x prefetched to L2, rows of Hconj prefetched to L1, register prefetch of the next row, x through L1, Hconj ring,
+// x rows by bulk copy, stage-1 twiddles by recurrence, lanes of the shuffle stage.  Each setting is the measured
+// winner of its A/B (DESIGN.md section 3 keeps the log, including the variants that lost and were deleted).
+using Plan64 = Plan<64, 16, 4, 1, 32, 2, 0, 0, 1>;
+using Plan128 = Plan<128, 16, 8, 1, 16, 2, 0, 0, 1>;
+using Plan256 = Plan<256, 16, 16, 1, 8, 2, 0, 1, 1>;
+using Plan512 = Plan<512, 32, 16, 1, 8, 1, 1, 1>;
+using Plan1024 = Plan<1024, 32, 32, 1, 4, 1, 0, 1, 0, false, true, true>;
+#ifndef LSMRC_SHUFFLE_PLANS  // development A/B switch: 0 = the round-1 three-stage plans for 2048/4096 points
+#define LSMRC_SHUFFLE_PLANS 1
 #endif
-#ifndef LSMRC_1024_NBUF
-#define LSMRC_1024_NBUF 1
+#if LSMRC_SHUFFLE_PLANS
+using Plan2048 = Plan<2048, 32, 32, 1, 2, 1, 1, 0, 0, false, false, false, true, 2>;
+using Plan4096 = Plan<4096, 32, 32, 1, 1, 1, 1, 0, 0, false, false, false, true, 4>;
+#else
+using Plan2048 = Plan<2048, 32, 16, 4, 2, 1, 1, 0, 0, false, false, false, true>;
+using Plan4096 = Plan<4096, 32, 32, 4, 1, 1, 1, 0, 0, false, false, false, true>;
 #endif
-// (with X_TMA the rows arrive by bulk copy a third of a row ahead; an extra L2 prefetch costs 4 %)
-#ifndef LSMRC_1024_PFX
-#define LSMRC_1024_PFX 0
-#endif
-#ifndef LSMRC_1024_PFH
-#define LSMRC_1024_PFH 1
-#endif
-#ifndef LSMRC_1024_MINB
-#define LSMRC_1024_MINB 3
-#endif
-#ifndef LSMRC_1024_REGPF
-#define LSMRC_1024_REGPF 0
-#endif
-#ifndef LSMRC_1024_XL1
-#define LSMRC_1024_XL1 false
-#endif
-#ifndef LSMRC_1024_HRING
-#define LSMRC_1024_HRING true
-#endif
-// antenna rows by bulk async copy into the exchange tile: 2.65 -> 2.48 ms per 256 frames (c2)
-#ifndef LSMRC_1024_XTMA
-#define LSMRC_1024_XTMA true
-#endif
+constexpr int kMinBlocks = 3;  // 3 CTAs (12 warps) per SM at 168 registers: measured best for every size
 
-// knobs of the small plans (64..512 points): rows of x prefetched to L2, rows of Hconj prefetched to L1,
-// register double-buffering of the next row
-#ifndef LSMRC_SMALL_PFX
-#define LSMRC_SMALL_PFX 0
-#endif
-#ifndef LSMRC_SMALL_PFH
-#define LSMRC_SMALL_PFH 0
-#endif
-#ifndef LSMRC_SMALL_REGPF
-#define LSMRC_SMALL_REGPF 1
-#endif
-// measured on c1/c5 (16384 frames): 3 CTAs/SM at 168 registers beat 4 at 128 by 15-25 % (the FFT working set no
-// longer spills) and loading the next row into registers behind stage 1 adds another 5-10 %
-#ifndef LSMRC_SMALL_MINB
-#define LSMRC_SMALL_MINB 3
-#endif
-// 512 points (measured, 32 antennas x 1024 frames): single tile buffer + next x row prefetched to L2 + next
-// Hconj row prefetched to L1: 3.62 -> 4.95 TB/s algorithmic
-#ifndef LSMRC_512_PFX
-#define LSMRC_512_PFX 1
-#endif
-#ifndef LSMRC_512_PFH
-#define LSMRC_512_PFH 1
-#endif
-#ifndef LSMRC_512_NBUF
-#define LSMRC_512_NBUF 1
-#endif
-#ifndef LSMRC_SMALL_NBUF
-#define LSMRC_SMALL_NBUF 2
-#endif
-#ifndef LSMRC_64_TEAMS
-#define LSMRC_64_TEAMS 32
-#endif
-#ifndef LSMRC_128_TEAMS
-#define LSMRC_128_TEAMS 16
-#endif
-// 256 points: prefetching the next Hconj row into L1 pays (+10 %, 32 antennas x 2048 frames); it does not for 64/128
-#ifndef LSMRC_256_PFH
-#define LSMRC_256_PFH 1
-#endif
-// knobs of the 2048- and 4096-point plans
-#ifndef LSMRC_2048_TEAMS
-#define LSMRC_2048_TEAMS 2
-#endif
-#ifndef LSMRC_2048_NBUF
-#define LSMRC_2048_NBUF 1
-#endif
-#ifndef LSMRC_2048_PFX
-#define LSMRC_2048_PFX 1
-#endif
-#ifndef LSMRC_2048_PFH
-#define LSMRC_2048_PFH 0
-#endif
-#ifndef LSMRC_2048_HRING
-#define LSMRC_2048_HRING false
-#endif
-#ifndef LSMRC_2048_MINB
-#define LSMRC_2048_MINB 3
-#endif
-#ifndef LSMRC_4096_TEAMS
-#define LSMRC_4096_TEAMS 1
-#endif
-#ifndef LSMRC_4096_NBUF
-#define LSMRC_4096_NBUF 1
-#endif
-#ifndef LSMRC_4096_PFX
-#define LSMRC_4096_PFX 1
-#endif
-#ifndef LSMRC_4096_PFH
-#define LSMRC_4096_PFH 0
-#endif
-#ifndef LSMRC_4096_HRING
-#define LSMRC_4096_HRING false
-#endif
-#ifndef LSMRC_4096_MINB
-#define LSMRC_4096_MINB 3
-#endif
-#ifndef LSMRC_512_XTMA
-#define LSMRC_512_XTMA false
-#endif
-#ifndef LSMRC_512_TWREC
-#define LSMRC_512_TWREC false
-#endif
-// three-stage plans are bound by the shared-memory/LSU pipe: generating the stage-1 twiddles in registers
-// instead of loading them is worth +2 % (c3) / +3 % (c4); it costs 10 % at 512 points and nothing at 1024
-#ifndef LSMRC_2048_TWREC
-#define LSMRC_2048_TWREC true
-#endif
-#ifndef LSMRC_4096_TWREC
-#define LSMRC_4096_TWREC true
-#endif
-#ifndef LSMRC_2048_XTMA
-#define LSMRC_2048_XTMA false
-#endif
-#ifndef LSMRC_4096_XTMA
-#define LSMRC_4096_XTMA false
+// LSMRC_ONLY_N=<size> (development): instantiate the kernels of one FFT size only -- a full build takes 85 s
+#ifdef LSMRC_ONLY_N
+#define LSMRC_HAVE(n) ((n) == LSMRC_ONLY_N)
+#else
+#define LSMRC_HAVE(n) 1
 #endif
 
 // One plan per FFT size (64..4096).  N/P threads own a row; see lsmrc_kernels.cuh.
 const PlanOps* find_plan(int N)
 {
     static const PlanOps plans[] = {
-        make_ops<Plan<64, 16, 4, 1, LSMRC_64_TEAMS, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
-        make_ops<Plan<128, 16, 8, 1, LSMRC_128_TEAMS, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_SMALL_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
-        make_ops<Plan<256, 16, 16, 1, 8, LSMRC_SMALL_NBUF, LSMRC_SMALL_PFX, LSMRC_256_PFH, LSMRC_SMALL_REGPF>, LSMRC_SMALL_MINB>(),
-        make_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA, LSMRC_512_TWREC>, 3>(),
-        make_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>, LSMRC_1024_MINB>(),
-        make_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA, LSMRC_2048_TWREC>, LSMRC_2048_MINB>(),
-        make_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA, LSMRC_4096_TWREC>, LSMRC_4096_MINB>(),
+#if LSMRC_HAVE(64)
+        make_ops<Plan64, kMinBlocks>(),
+#endif
+#if LSMRC_HAVE(128)
+        make_ops<Plan128, kMinBlocks>(),
+#endif
+#if LSMRC_HAVE(256)
+        make_ops<Plan256, kMinBlocks>(),
+#endif
+#if LSMRC_HAVE(512)
+        make_ops<Plan512, kMinBlocks>(),
+#endif
+#if LSMRC_HAVE(1024)
+        make_ops<Plan1024, kMinBlocks>(),
+#endif
+#if LSMRC_HAVE(2048)
+        make_ops<Plan2048, kMinBlocks>(),
+#endif
+#if LSMRC_HAVE(4096)
+        make_ops<Plan4096, kMinBlocks>(),
+#endif
     };
     for (const PlanOps& o : plans)
         if (o.N == N) return &o;
     return nullptr;
 }
 
-// Dedicated pilot plans (sizes not listed use the main plan's MODE_PILOT instantiation).
+// Dedicated pilot plans (sizes not listed use the main plan's MODE_PILOT instantiation).  Only for plans whose
+// channel rows are in bin order: the shuffle-stage plans need the pilot kernel to share their slot layout.
 const PilotOps* find_pilot_plan(int N)
 {
+#if !LSMRC_SHUFFLE_PLANS
     static const PilotOps plans[] = {
+#if LSMRC_HAVE(2048)
         make_pilot_ops<Plan<2048, 16, 16, 8, 2, 1, 1, 0>, 2>(),
+#endif
+#if LSMRC_HAVE(4096)
         make_pilot_ops<Plan<4096, 16, 16, 16, 1, 1, 1, 0>, 2>(),
+#endif
     };
-    if (!LSMRC_PILOT_PLANS) return nullptr;
     for (const PilotOps& o : plans)
         if (o.N == N) return &o;
+#endif
+    (void)N;
     return nullptr;
 }
 
@@ -434,13 +373,27 @@ const PilotOps* find_pilot_plan(int N)
 const OneshotOps* find_oneshot_plan(int N)
 {
     static const OneshotOps plans[] = {
+#if LSMRC_HAVE(64)
         make_oneshot_ops<Plan<64, 8, 8, 1, 16, 2>>(),
+#endif
+#if LSMRC_HAVE(128)
         make_oneshot_ops<Plan<128, 8, 4, 4, 16, 1>>(),
+#endif
+#if LSMRC_HAVE(256)
         make_oneshot_ops<Plan<256, 8, 8, 4, 8, 1>>(),
-        make_oneshot_ops<Plan<512, 32, 16, 1, 8, LSMRC_512_NBUF, LSMRC_512_PFX, LSMRC_512_PFH, 0, false, false, LSMRC_512_XTMA, LSMRC_512_TWREC>>(),
-        make_oneshot_ops<Plan<1024, 32, 32, 1, LSMRC_1024_TEAMS, LSMRC_1024_NBUF, LSMRC_1024_PFX, LSMRC_1024_PFH, LSMRC_1024_REGPF, LSMRC_1024_XL1, LSMRC_1024_HRING, LSMRC_1024_XTMA>>(),
-        make_oneshot_ops<Plan<2048, 32, 16, 4, LSMRC_2048_TEAMS, LSMRC_2048_NBUF, LSMRC_2048_PFX, LSMRC_2048_PFH, 0, false, LSMRC_2048_HRING, LSMRC_2048_XTMA, LSMRC_2048_TWREC>>(),
-        make_oneshot_ops<Plan<4096, 32, 32, 4, LSMRC_4096_TEAMS, LSMRC_4096_NBUF, LSMRC_4096_PFX, LSMRC_4096_PFH, 0, false, LSMRC_4096_HRING, LSMRC_4096_XTMA, LSMRC_4096_TWREC>>(),
+#endif
+#if LSMRC_HAVE(512)
+        make_oneshot_ops<Plan512>(),
+#endif
+#if LSMRC_HAVE(1024)
+        make_oneshot_ops<Plan1024>(),
+#endif
+#if LSMRC_HAVE(2048)
+        make_oneshot_ops<Plan2048>(),
+#endif
+#if LSMRC_HAVE(4096)
+        make_oneshot_ops<Plan4096>(),
+#endif
     };
     for (const OneshotOps& o : plans)
         if (o.N == N) return &o;

@@ -44,12 +44,12 @@
 
 #include "fft_radix.cuh"
 
-#ifndef LSMRC_H_STAGES
-#define LSMRC_H_STAGES 3
+// development A/B switch of lsmrc_data_sh: antenna rows by bulk copy into the tile (1) or by plain loads (0)
+#ifndef LSMRC_SH_XMODE
+#define LSMRC_SH_XMODE 1
 #endif
-#ifndef LSMRC_TW_CHUNK
-#define LSMRC_TW_CHUNK 4
-#endif
+constexpr int kHStages = 3;  // depth of the Hconj ring (rows)
+constexpr int kTwChunk = 4;  // inter-stage twiddles fetched this many at a time, one chunk ahead of their use
 
 namespace lsmrc {
 
@@ -109,8 +109,20 @@ struct KernelParams {
 };
 
 template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false,
-          bool X_TMA_ = false, bool TW_REC_ = false>
+          bool X_TMA_ = false, bool TW_REC_ = false, int SH_ = 1>
 struct Plan {
+    // SH > 1 (2 or 4; N = 32 * 32 * SH, teams of SH warps): the LAST radix-SH stage runs across the SH adjacent lanes
+    // of a warp through shuffles instead of a second shared-memory exchange (see row_fft).  Measured on B200
+    // (tools/ubench_lsu.cu, profiles/r02_ubench_lsu.txt): a 64-bit LDS/STS costs 2 clocks of the SM's L1/LSU data
+    // pipe per warp, a SHFL about 0.55, and that pipe is what bounds these kernels.  Consequences of the layout:
+    //  * thread (k1, q), q = lane % SH, ends up with bins k1 + 32*k2 + 1024*k3 for 32/SH values of k2 and all k3
+    //    (bin_of below), so the per-antenna channel rows are kept slot-major ([slot][thread], hpos below) to stay
+    //    coalesced, and
+    //  * some outputs carry a unit factor u in {1, -1, i, -i} that depends on (slot, lane) only (unfix/fix below).
+    //    The pilot kernel stores conj(H) computed from the same factored outputs, so u cancels in Y * conj(H);
+    //    only exported values (Hconj in the reference layout, the stand-alone FFT) are corrected.
+    static constexpr int SH = SH_;
+    static_assert(SH_ == 1 || ((SH_ == 2 || SH_ == 4) && P_ == 32 && R2_ == 32 && R3_ == 1), "shuffle stage: N = 32*32*SH");
     // TW_REC (data kernel, P = 32): the inter-stage twiddles W^(t*k1) are not read from the shared-memory table but
     // generated in registers by the recurrence w(k1+1) = w(k1) * W^t, restarted from exact table values every 8
     // steps (4 register pairs for the whole kernel, one extra complex multiply per twiddle, <= 7 accumulated
@@ -131,27 +143,33 @@ struct Plan {
     // H_RING: the TEAMS teams of a CTA work on TEAMS data symbols of ONE frame and share each
     // Hconj row through a shared-memory ring filled by bulk async copies (TMA) on mbarriers
     static constexpr bool H_RING = H_RING_;
-    static constexpr int H_STAGES = LSMRC_H_STAGES;   // ring depth
-    static constexpr int H_AHEAD = LSMRC_H_STAGES - 2; // rows kept in flight ahead of the row being consumed
-    static constexpr int TW_CHUNK = (P_ >= 8) ? LSMRC_TW_CHUNK : P_;  // inter-stage twiddles fetched this many at a time
+    static constexpr int H_STAGES = kHStages;   // ring depth
+    static constexpr int H_AHEAD = kHStages - 2; // rows kept in flight ahead of the row being consumed
+    static constexpr int TW_CHUNK = (P_ >= 8) ? kTwChunk : P_;  // inter-stage twiddles fetched this many at a time
     static constexpr int HRING = H_RING_ ? H_STAGES * N_ : 0;  // complex elements
     // PF_X: rows ahead whose antenna-samples are prefetched into L2; PF_H: rows ahead whose
     // Hconj row is prefetched into L1 (0 = off)
     static constexpr int PF_X = PF_X_, PF_H = PF_H_;
     static constexpr int N = N_, P = P_, R2 = R2_, R3 = R3_, TEAMS = TEAMS_, NBUF = NBUF_;
     static constexpr int T = N / P;        // threads per team == M1 (points per row of the tile)
-    static constexpr int ROW = T + 1;      // padded tile row (complex elements)
+    // Tile row pitch (complex elements).  Plain plans pad the row by one element: their stage-2 read has lanes k1 at
+    // k1*ROW + const, conflict-free for odd ROW.  Shuffle-stage plans keep the rows dense (so that a whole antenna
+    // row lands in the tile with ONE linear bulk copy) and swizzle the columns instead: element (r, c) sits in column
+    // c ^ swz(r), swz(r) = SH * (r mod 16/SH).  Their stage-2 read has lanes (k1, q) on column n2*SH + q of row k1,
+    // i.e. on bank pair ((n2 ^ k1) mod 16/SH) * SH + q: distinct over the 16 lanes of a 64-bit wavefront.
+    static constexpr int ROW = (SH_ > 1) ? T : T + 1;
+    static __host__ __device__ constexpr int swz(int r) { return (SH_ > 1) ? SH_ * (r % (16 / SH_)) : 0; }
     // index of element (r, c) of the tile
-    static __device__ __forceinline__ int at(int r, int c) { return r * ROW + c; }
+    static __device__ __forceinline__ int at(int r, int c) { return r * ROW + (c ^ swz(r)); }
     static_assert(!X_TMA_ || (NBUF_ == 1 && N_ / P_ >= 16), "X_TMA: one tile per team, teams of at least half a warp");
     static_assert(!X_TMA_ || ((P_ * (N_ / P_ + 1)) % 2 == 0), "X_TMA: team tiles must stay 16-byte aligned");
     static constexpr int NB2 = P / R2;     // stage-2 butterflies per thread
     static constexpr int NB3 = P / R3;     // stage-3 butterflies per thread (R3 > 1)
-    static constexpr int RL = (R3 > 1) ? R3 : R2;  // radix of the last stage
+    static constexpr int RL = (R3 > 1) ? R3 : R2;  // radix of the last shared-memory stage
     static constexpr int NBL = P / RL;             // last-stage butterflies per thread
     static constexpr int THREADS = T * TEAMS;
     static constexpr int TW1 = (P - 1) * T;
-    static constexpr int TW2 = (R3 > 1) ? (R2 - 1) * R3 : 0;
+    static constexpr int TW2 = (SH_ > 1) ? 32 * SH_ : (R3 > 1) ? (R2 - 1) * R3 : 0;  // SH: W_T^(q*k2) at [k2][q]
     static constexpr int TWN = TW1 + TW2;
     static constexpr int TILE = P * ROW;   // complex elements per tile
     // Per-team tile block.  Teams narrower than a half-warp share 64-bit shared-memory wavefronts
@@ -162,7 +180,50 @@ struct Plan {
     static constexpr int TEAM_STRIDE = (T >= 16) ? TEAM_TILES : TEAM_TILES + ((T - TEAM_TILES % 16) + 16) % 16;
     static constexpr size_t SMEM_BYTES = sizeof(float2) * (size_t)(TWN + HRING + TEAMS * TEAM_STRIDE);
     static_assert(!H_RING_ || TWN % 2 == 0, "ring rows must stay 16-byte aligned");
-    static_assert(P * R2 * R3 == N, "plan must factor N");
+    static_assert(P * R2 * R3 * SH_ == N, "plan must factor N");
+    // FFT bin of accumulator slot `sl` of thread `t` of a team (the order the sink of row_fft is called in)
+    static __device__ __forceinline__ int bin_of(int sl, int t)
+    {
+        if constexpr (SH_ == 1) {
+            return t + T * (sl / RL) + (N / RL) * (sl % RL);
+        } else {
+            const int lane = t & 31, q = lane % SH_, k1 = lane / SH_ + (32 / SH_) * (t >> 5);
+            const int c = sl & 1, kk = brev<32>(sl & ~1);
+            const int k2 = kk + 16 * (SH_ == 2 ? q : (q >> 1));
+            const int k3 = SH_ == 2 ? c : (q & 1) + 2 * c;
+            return k1 + 32 * k2 + 1024 * k3;
+        }
+    }
+    // position of that bin's conj(H) inside a channel row of hwork (N entries per antenna)
+    static __device__ __forceinline__ int hpos(int sl, int t, int bin) { return SH_ == 1 ? bin : sl * T + t; }
+    // row_fft hands slot `sl` of thread `t` the value y' = u * Y; unfix() returns Y = conj(u) * y', refix() u * v
+    template <bool CONJ>
+    static __device__ __forceinline__ float2 unit_mul(int sl, int t, float2 v)
+    {
+        if constexpr (SH_ == 1) {
+            return v;
+        } else if constexpr (SH_ == 2) {
+            const bool neg = (sl & 1) && (t & 1);
+            return neg ? make_float2(-v.x, -v.y) : v;
+        } else {
+            if (!(t & 1)) return v;
+            // u = i * kappa (kappa = +-1): u*v = kappa*(-v.y, v.x), conj(u)*v = kappa*(v.y, -v.x)
+            const float kappa = (((t >> 1) & 1) != (sl & 1)) ? -1.f : 1.f;
+            return CONJ ? make_float2(kappa * v.y, -kappa * v.x) : make_float2(-kappa * v.y, kappa * v.x);
+        }
+    }
+    static __device__ __forceinline__ float2 unfix(int sl, int t, float2 v) { return unit_mul<true>(sl, t, v); }
+    static __device__ __forceinline__ float2 refix(int sl, int t, float2 v) { return unit_mul<false>(sl, t, v); }
+    // stage-1 outputs of thread t are written with this sign: it swaps, per reading lane, which register of a
+    // pair (2j, 2j+1) the last stage-2 butterfly leaves X[k] and X[k+16] in, so that every lane of a shuffle group
+    // keeps register 2j and sends register 2j+1 without a select (the sign of the odd-indexed inputs of a
+    // decimation-in-time transform flips the sign of the last stage's twiddles)
+    static __device__ __forceinline__ float stage1_sign(int t)
+    {
+        if constexpr (SH_ == 2) return ((t & 3) == 3) ? -1.f : 1.f;
+        else if constexpr (SH_ == 4) return ((t & 6) == 6) ? -1.f : 1.f;
+        else return 1.f;
+    }
     static_assert(P >= R2 && P >= R3, "thread must own whole butterflies");
     static_assert(THREADS <= 1024, "block too large");
     static_assert(T <= 32 || TEAMS <= 15, "named barriers 1..15");
@@ -334,6 +395,95 @@ __device__ __forceinline__ void soft_symbol(float re, float im, float rho, float
 // [0,P) is the thread-local accumulator index and bin = c + (N/RL)*j is the FFT bin.
 // If x_next != nullptr the next row is loaded into `v` as soon as stage 1 has consumed it,
 // so its HBM latency hides behind stage 2/3 and the MRC of this row (register prefetch).
+// Last stage of the shuffle-stage plans for a batch of JB register pairs: the radix-SH transform over the SH adjacent
+// lanes q = lane % SH.  keep[i] / send[i] are registers 2j / 2j+1 of the stage-2 transform (already twiddled; which
+// k2 they hold depends on the lane, see Plan::stage1_sign); A[i] / B[i] are the outputs of slots 2j / 2j+1, each
+// times the slot's unit factor (Plan::unit_mul).  All shuffles of a round are issued back to back so that their
+// latencies overlap.
+//   SH = 2: one round, partner lane ^ 1:            A = keep + r, B = keep - r
+//   SH = 4: decimation in time over q = 2*q1 + q0.  Round 1, partner lane ^ 2 (same q0):
+//             p = keep + s0*r1, m = keep - s0*r1, s0 = +1 on even lanes, -1 on odd lanes
+//             (even lanes: p = E+, m = sigma1*E-; odd lanes: p = sigma1*O-, m = O+; sigma1 = +-1 by q1), so that every
+//             lane keeps p and sends m; round 2, partner lane ^ 1:
+//             even lanes A = p + r2 = X[k3 = 0], B = p - r2 = X[2];  odd lanes A = p + i*r2 = i*sigma1*X[1],
+//             B = p - i*r2 = -i*sigma1*X[3]
+template <int SH, int JB>
+__device__ __forceinline__ void sh_radix_batch(const float2 (&keep)[JB], const float2 (&send)[JB], int q, float2 (&A)[JB], float2 (&B)[JB])
+{
+    if constexpr (SH == 2) {
+        float2 r1[JB];
+#pragma unroll
+        for (int i = 0; i < JB; ++i) {
+            r1[i].x = __shfl_xor_sync(0xffffffffu, send[i].x, 1);
+            r1[i].y = __shfl_xor_sync(0xffffffffu, send[i].y, 1);
+        }
+#pragma unroll
+        for (int i = 0; i < JB; ++i) {
+            A[i] = cadd(keep[i], r1[i]);
+            B[i] = csub(keep[i], r1[i]);
+        }
+    } else {
+        const bool odd = (q & 1) != 0;
+        const float s0 = odd ? -1.f : 1.f;
+        const float2 sp = make_float2(s0, s0), sm = make_float2(-s0, -s0);
+        // odd lanes: p + i*r2 = p + swp(r2) * (-1, 1)
+        const float2 kp = odd ? make_float2(-1.f, 1.f) : make_float2(1.f, 1.f);
+        const float2 km = make_float2(-kp.x, -kp.y);
+        float2 r1[JB], pp[JB], mm[JB], r2[JB];
+#pragma unroll
+        for (int i = 0; i < JB; ++i) {
+            r1[i].x = __shfl_xor_sync(0xffffffffu, send[i].x, 2);
+            r1[i].y = __shfl_xor_sync(0xffffffffu, send[i].y, 2);
+        }
+#pragma unroll
+        for (int i = 0; i < JB; ++i) {
+            pp[i] = __ffma2_rn(r1[i], sp, keep[i]);
+            mm[i] = __ffma2_rn(r1[i], sm, keep[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < JB; ++i) {
+            r2[i].x = __shfl_xor_sync(0xffffffffu, mm[i].x, 1);
+            r2[i].y = __shfl_xor_sync(0xffffffffu, mm[i].y, 1);
+        }
+#pragma unroll
+        for (int i = 0; i < JB; ++i) {
+            const float2 rr = odd ? swp(r2[i]) : r2[i];
+            A[i] = __ffma2_rn(rr, kp, pp[i]);
+            B[i] = __ffma2_rn(rr, km, pp[i]);
+        }
+    }
+}
+
+constexpr int kShBatch = 4;  // register pairs per shuffle batch (= one 8-slot chunk of the Hconj ring)
+
+// twiddles W_T^(q*k2) of the 2*JB registers of batch jb: register r holds k2 = brev(r & ~1) + 16*(hi ^ (r & 1))
+template <int SH, int JB>
+__device__ __forceinline__ void sh_load_twiddles(float2 (&tw)[2 * JB], const float2* twq, int hi, int jb)
+{
+#pragma unroll
+    for (int i = 0; i < 2 * JB; ++i) {
+        const int r = 2 * JB * jb + i;
+        tw[i] = lds_volatile(twq + (brev<32>(r & ~1) + 16 * (hi ^ (r & 1))) * SH);
+    }
+}
+
+// stage-2 operands of thread (k1, q) of a shuffle-stage plan: element n2*SH + q of tile row k1, n2 = 0..31, out of the
+// swizzled tile (Plan::at): column SH*(n2 ^ g) + q with g = k1 mod G, G = 16/SH.  Writing n2 = G*m + i, the address is
+// (row + q + SH*(i ^ g)) + 16*m: G base pointers and compile-time offsets.
+template <class PL>
+__device__ __forceinline__ void sh_stage2_read(float2 (&u)[32], const float2* __restrict__ tile, int k1, int q)
+{
+    constexpr int SH = PL::SH, G = 16 / SH;
+    const int g = k1 % G;
+    const float2* row = tile + k1 * PL::ROW + q;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const float2* base = row + SH * (i ^ g);
+#pragma unroll
+        for (int m = 0; m < 32 / G; ++m) u[G * m + i] = base[16 * m];
+    }
+}
+
 struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
@@ -352,15 +502,20 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
         // tw_regs[0] = W^t; tw_regs[1..3] = exact W^(8t), W^(16t), W^(24t).  The step is laundered through an empty
         // asm: the chain depends on kernel-lifetime values only, and left visible the compiler hoists all 31
         // products out of the row loop and spills them.
+        // Shuffle-stage plans: every stage-1 output of this thread carries the sign stage1_sign(t) (see Plan); the
+        // restart values tw_regs[1..3] and the chain's start tw_regs[4] have it folded in, the step tw_regs[0] has not.
         float2 w1 = tw_regs[0];
         asm volatile("" : "+f"(w1.x), "+f"(w1.y));
-        float2 w = w1;
+        float2 w = (PL::SH > 1) ? tw_regs[4] : w1;
 #pragma unroll
         for (int k1 = 0; k1 < P; ++k1) {
             float2 val = v[brev<P>(k1)];
             if (k1 > 0) {
                 val = cmul(val, w);
                 if (k1 + 1 < P) w = ((k1 + 1) % 8 == 0) ? tw_regs[(k1 + 1) / 8] : cmul(w, w1);
+            } else if (PL::SH > 1) {
+                const float sg = PL::stage1_sign(t);
+                val = __fmul2_rn(val, make_float2(sg, sg));
             }
             tile[PL::at(k1, t)] = val;
             if (k1 % 4 == 3) asm volatile("" ::: "memory");  // keep the twiddle chain from running ahead of its use
@@ -387,7 +542,12 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
         for (int j = 0; j < TWC; ++j) {
             const int k1 = c * TWC + j;
             float2 val = v[brev<P>(k1)];
-            if (k1 > 0) val = cmul(val, twa[j]);
+            if (k1 > 0) {
+                val = cmul(val, twa[j]);  // (shuffle-stage plans: the table carries stage1_sign(t))
+            } else if (PL::SH > 1) {
+                const float sg = PL::stage1_sign(t);
+                val = __fmul2_rn(val, make_float2(sg, sg));
+            }
             tile[PL::at(k1, t)] = val;
         }
         asm volatile("" ::: "memory");
@@ -397,6 +557,47 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
     }
     if (x_next != nullptr) row_load<PL>(v, x_next, t);
     team_sync<PL>(team);
+    if constexpr (PL::SH > 1) {
+        // ---- shuffle-stage plans: N = 32 * 32 * SH.  Thread (k1, q), q = lane % SH, transforms the 32 samples
+        // t2 = n2*SH + q of row k1 of the tile; the remaining radix-SH stage over q runs across the SH adjacent lanes.
+        // A plain transpose would make every lane choose which half of its registers to send (selects); instead the
+        // sign trick of Plan::stage1_sign leaves U[kk + 16*hi] in register 2j ("keep") and U[kk + 16*(1-hi)] in
+        // 2j+1 ("send"), hi = the high bit of q, so the choice is the same instruction in every lane.
+        constexpr int SH = PL::SH;
+        const int lane = t & 31;
+        const int q = lane % SH;
+        const int k1 = lane / SH + (32 / SH) * (t >> 5);
+        const int hi = (SH == 2) ? q : (q >> 1);
+        float2 u[32];
+        sh_stage2_read<PL>(u, tile, k1, q);
+        after_reads();  // the tile is free from here on
+        fft_reg<32>(u);
+        // twiddles W_T^(q*k2), fetched one batch ahead of their multiplies; then the cross-lane radix-SH stage
+        constexpr int JB = kShBatch;
+        const float2* twq = s_tw2 + q;
+        float2 tw[2 * JB], twn[2 * JB];
+        sh_load_twiddles<SH, JB>(tw, twq, hi, 0);
+#pragma unroll
+        for (int jb = 0; jb < 16 / JB; ++jb) {
+            if (jb + 1 < 16 / JB) sh_load_twiddles<SH, JB>(twn, twq, hi, jb + 1);
+            asm volatile("" ::: "memory");
+            float2 keep[JB], send[JB], A[JB], B[JB];
+#pragma unroll
+            for (int i = 0; i < JB; ++i) {
+                keep[i] = cmul(u[2 * (JB * jb + i)], tw[2 * i]);
+                send[i] = cmul(u[2 * (JB * jb + i) + 1], tw[2 * i + 1]);
+            }
+            sh_radix_batch<SH, JB>(keep, send, q, A, B);
+#pragma unroll
+            for (int i = 0; i < JB; ++i) {
+                const int sl = 2 * (JB * jb + i);
+                sink(sl, PL::bin_of(sl, t), A[i]);
+                sink(sl + 1, PL::bin_of(sl + 1, t), B[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2 * JB; ++i) tw[i] = twn[i];
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < PL::NB2; ++i) {
         const int b = t + T * i;
@@ -474,6 +675,7 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
             for (int k3 = 0; k3 < R3; ++k3) sink(i * R3 + k3, c + (PL::N / R3) * k3, w[brev<R3>(k3)]);
         }
     }
+    }  // plans without a shuffle stage
     if constexpr (PL::NBUF == 1) team_sync<PL>(team);
 }
 
@@ -495,16 +697,14 @@ __device__ __forceinline__ void mrc_finish(const KernelParams& p, const float2 (
         float einv[P];
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
-            const int i = sl / PL::RL, j = sl % PL::RL;
-            const int bin = t + T * i + (N / PL::RL) * j;
+            const int bin = PL::bin_of(sl, t);
             const int idx = bin > 0 ? bin - 1 : 0;
             einv[sl] = E_SHARED ? e_row[idx] : __ldg(e_row + idx);
         }
         team_sync<PL>(team);  // everyone is done reading the last tile before it is reused
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
-            const int i = sl / PL::RL, j = sl % PL::RL;
-            const int bin = t + T * i + (N / PL::RL) * j;
+            const int bin = PL::bin_of(sl, t);
             if (bin > 0) {
                 // one reciprocal, two multiplies (<= 2 ulp from the reference's two divisions,
                 // far inside the 1e-5 parity tolerance)
@@ -573,8 +773,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             row_load<PL>(v, p.rx + (long long)row * p.ant_stride + p.cp, t);
             float2* out = p.combined + (long long)row * N;
             team_sync<PL>(team);
-            row_fft<PL>(v, nullptr, my_tiles, s_tw1, s_tw2, t, team, [&](int, int bin, float2 y) {
-                if (ok) out[bin] = y;
+            row_fft<PL>(v, nullptr, my_tiles, s_tw1, s_tw2, t, team, [&](int sl, int bin, float2 y) {
+                if (ok) out[bin] = PL::unfix(sl, t, y);
             });
             team_sync<PL>(team);
         }
@@ -591,8 +791,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         float xden[P];  // 1/|X|^2, hoisted: cpuLS.hpp:240-241 divides by |X|^2 per element (<= 1 ulp apart)
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
-            const int i = sl / PL::RL, j = sl % PL::RL;
-            const int bin = t + T * i + (N / PL::RL) * j;
+            const int bin = PL::bin_of(sl, t);
             xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
             xden[sl] = 1.0f / (xp[sl].x * xp[sl].x + xp[sl].y * xp[sl].y);
         }
@@ -628,10 +827,12 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                             const float re = (z.x * X.x + z.y * X.y) * xden[sl];
                             const float im = (z.y * X.x - z.x * X.y) * xden[sl];
                             if (a_ok) {
+                                // (shuffle-stage plans: z carries the unit factor of its slot, and so does the hc the
+                                // data kernel will multiply its equally factored outputs with; the exported copy is exact)
                                 const float2 hc = (bin > 0) ? make_float2(re, -im) : make_float2(0.f, 0.f);
-                                hw_row[bin] = hc;
+                                hw_row[PL::hpos(sl, t, bin)] = hc;
                                 if (bin > 0) {
-                                    if (hc_row) hc_row[bin - 1] = hc;
+                                    if (hc_row) hc_row[bin - 1] = PL::refix(sl, t, hc);
                                     e[sl] += re * re + im * im;  // cpuLS.hpp:211-228
                                 }
                             }
@@ -642,8 +843,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         float* s_e = reinterpret_cast<float*>(s_tiles);  // [TEAMS][N]
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
-            const int i = sl / PL::RL, j = sl % PL::RL;
-            const int bin = t + T * i + (N / PL::RL) * j;
+            const int bin = PL::bin_of(sl, t);
             s_e[team * N + bin] = e[sl];
         }
         __syncthreads();
@@ -731,8 +931,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         float xden[P];
 #pragma unroll
         for (int sl = 0; sl < P; ++sl) {
-            const int i = sl / PL::RL, j = sl % PL::RL;
-            const int bin = t + T * i + (N / PL::RL) * j;
+            const int bin = PL::bin_of(sl, t);
             e[sl] = 0.f;
             xp[sl] = p.pilot_bin[bin > 0 ? bin - 1 : 0];
         }
@@ -760,10 +959,10 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                 const float im = (z.y * X.x - z.x * X.y) * xden[sl];
                 if (a_ok) {
                     const float2 hc = (bin > 0) ? make_float2(re, -im) : make_float2(0.f, 0.f);
-                    sh_row[bin] = hc;
+                    sh_row[bin] = hc;  // (read back below by the same thread for the same slot: unit factors cancel)
                     if (writer) {
-                        hw_row[bin] = hc;
-                        if (bin > 0 && hc_row) hc_row[bin - 1] = hc;
+                        hw_row[PL::hpos(sl, t, bin)] = hc;
+                        if (bin > 0 && hc_row) hc_row[bin - 1] = PL::refix(sl, t, hc);
                     }
                     if (bin > 0) e[sl] += re * re + im * im;
                 }
@@ -786,8 +985,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             const int part = team / TPW;
 #pragma unroll
             for (int sl = 0; sl < P; ++sl) {
-                const int i = sl / PL::RL, j = sl % PL::RL;
-                const int bin = t + T * i + (N / PL::RL) * j;
+                const int bin = PL::bin_of(sl, t);
                 s_e[part * N + bin] = e[sl];
             }
         }
@@ -909,11 +1107,17 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             bulk_g2s(s_hring + sr * N, src_row, ROW_BYTES, &bar_full[sr]);
         };
 
-        float2 twr[PL::TW_REC ? 4 : 1];
+        float2 twr[PL::TW_REC ? 5 : 1];
         if constexpr (PL::TW_REC) {
             twr[0] = s_tw1[t];
 #pragma unroll
             for (int a = 1; a < 4; ++a) twr[a] = s_tw1[(8 * a - 1) * T + t];
+            // shuffle-stage plans: the table carries stage1_sign(t); the recurrence's step must not
+            twr[4] = twr[0];
+            if constexpr (PL::SH > 1) {
+                const float sg = PL::stage1_sign(t);
+                twr[0] = make_float2(sg * twr[0].x, sg * twr[0].y);
+            }
         }
         __shared__ int s_item;
         for (;;) {
@@ -1014,9 +1218,9 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                     mbar_wait(&bar_full[st], (uint32_t)((R / PL::H_STAGES) & 1));
                                     h_ready = true;
                                 }
-                                acc[sl] = cmac(acc[sl], h_src[bin], y);
+                                acc[sl] = cmac(acc[sl], h_src[PL::hpos(sl, t, bin)], y);
                             } else {
-                                const float2 h = __ldg(h_src + bin);
+                                const float2 h = __ldg(h_src + PL::hpos(sl, t, bin));
                                 if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
@@ -1061,6 +1265,194 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(my_tiles), valid, t, team);
         team_sync<PL>(team);  // the byte buffer aliases the tile the next item writes
         }  // work items
+    }
+}
+
+// ---- data kernel of the shuffle-stage plans (2048 and 4096 points) --------------------------------------------
+// Same job as MODE_DATA above (persistent CTAs, one team per (frame, data symbol), antenna loop with the MRC sums in
+// registers), restructured around what the shuffle stage frees up:
+//  * the tile is needed for ONE exchange only, so it is free as soon as the stage-2 operands have been read -- about
+//    40 % into a row.  From there the next antenna row is fetched into it by ONE linear bulk async copy (TMA): the
+//    rows of the tile are dense, a thread finds its 32 samples in its own column, and because the column swizzle of
+//    stage 1 (Plan::at) only moves data inside aligned groups of 16 lanes, "all samples read" before "stage 1
+//    written" is a warp-level dependency, not a team barrier.  The copy is issued by whichever warp of the team
+//    finishes its stage-2 reads last (a shared-memory counter), so nobody waits for anybody;
+//  * conj(H) of the antenna (slot-major row of hwork, Plan::hpos) is bulk-copied into a per-team buffer right
+//    after the one team barrier of the row -- passing it proves that every warp is done with the previous row's
+//    values -- and is needed only after the stage-2 transform.
+// Neither the samples nor the channel values are waited for on the scoreboard (35 % of all stall samples of the
+// round-1 kernels, profiles/r02_before_ncu_c4.txt), and a row costs one team barrier instead of three.
+// Shared memory per CTA: W_T^(q*k2) table + TEAMS x (channel row N + tile N) complex = 65 KB -> 3 CTAs per SM.
+// Rows that are not 16-byte aligned (odd prefix lengths) are read with plain 64-bit loads instead of bulk copies.
+template <class PL, int MINB>
+__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelParams p)
+{
+    constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, ROW = PL::ROW, TEAMS = PL::TEAMS;
+    constexpr int WPT = T / 32;  // warps per team
+    constexpr uint32_t ROW_BYTES = N * sizeof(float2);
+    static_assert(SH > 1 && PL::TW_REC && ROW == T, "shuffle-stage plans only");
+    extern __shared__ __align__(16) float2 smem[];
+    float2* s_tw2 = smem;                   // [32][SH]
+    float2* s_h = smem + PL::TW2;           // [TEAMS][N]   conj(H) of the current antenna, slot-major
+    float2* s_tiles = s_h + TEAMS * N;      // [TEAMS][32][T]
+    __shared__ __align__(8) uint64_t bar_x[TEAMS], bar_h[TEAMS];
+    __shared__ unsigned int s_readers[TEAMS];  // warps of the team that have read their stage-2 operands of this row
+    __shared__ int s_item;
+
+    const int team = threadIdx.x / T;
+    const int t = threadIdx.x % T;
+    const int lane = t & 31, wt = t >> 5;
+    float2* tile = s_tiles + team * N;
+    float2* hbuf = s_h + team * N;
+
+    for (int i = threadIdx.x; i < PL::TW2; i += PL::THREADS) s_tw2[i] = p.twiddles[PL::TW1 + i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TEAMS; ++i) {
+            mbar_init(&bar_x[i], 1);
+            mbar_init(&bar_h[i], 1);
+            s_readers[i] = 0u;
+        }
+        mbar_fence_init();
+    }
+    // stage-1 twiddle recurrence (see row_fft): step, three restart values, signed start
+    float2 twr[5];
+    twr[0] = p.twiddles[t];
+#pragma unroll
+    for (int a = 1; a < 4; ++a) twr[a] = p.twiddles[(8 * a - 1) * T + t];
+    twr[4] = twr[0];
+    const float sg = PL::stage1_sign(t);
+    twr[0] = make_float2(sg * twr[0].x, sg * twr[0].y);
+    const float2 sg2 = make_float2(sg, sg);
+    // this thread's stage-2 role: row k1 of the tile, lane position q of the shuffle group
+    const int q = lane % SH;
+    const int hi = (SH == 2) ? q : (q >> 1);
+    const int k1 = lane / SH + (32 / SH) * wt;
+    __syncthreads();
+
+    const long long n_work = (long long)p.n_frames * p.n_sym_work;
+    const int n_items = (int)((n_work + TEAMS - 1) / TEAMS);
+    const bool x_tma = p.x_tma != 0 && LSMRC_SH_XMODE != 0;
+    uint32_t x_phase = 0, h_phase = 0;
+
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned long long tk = atomicAdd(p.ticket, 1ULL);
+            s_item = tk < (unsigned long long)n_items ? (int)tk : -1;
+            if (s_item < 0) {
+                __threadfence();
+                if (atomicAdd(p.ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+                    p.ticket[0] = 0ULL;
+                    p.ticket[1] = 0ULL;
+                }
+            }
+        }
+        __syncthreads();
+        const int item = s_item;
+        __syncthreads();
+        if (item < 0) break;
+        long long work = (long long)item * TEAMS + team;
+        bool valid = work < n_work;
+        if (!valid) work = n_work - 1;
+        const int f = (int)(work / p.n_sym_work);
+        const int s = (int)(work % p.n_sym_work);
+        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)(p.first_sym + s) * p.sym_stride + p.cp;
+        const float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+        float2 acc[32];
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) acc[sl] = make_float2(0.f, 0.f);
+
+        if (x_tma && t == 0) {
+            fence_proxy_async();  // the tile doubled as the previous item's demap byte buffer
+            mbar_expect_tx(&bar_x[team], ROW_BYTES);
+            bulk_g2s(tile, x0, ROW_BYTES, &bar_x[team]);
+        }
+        for (int a = 0; a < p.n_ant; ++a) {
+            const float2* x_row = x0 + (long long)a * p.ant_stride;
+            float2 v[32];
+            if (x_tma) {
+                mbar_wait(&bar_x[team], x_phase);
+                x_phase ^= 1u;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) v[n1] = tile[n1 * T + t];  // as the copy laid the row out: linear
+                __syncwarp();  // stage 1 writes into columns of this warp's lanes only
+            } else {
+                row_load<PL>(v, x_row, t);
+                if (a + 1 < p.n_ant) prefetch_row<T, false>(x_row + p.ant_stride, N, t);
+            }
+            // ---- stage 1: 32-point transform over n1, twiddle W_N^(t*k1) by recurrence, into the swizzled tile
+            fft_reg<32>(v);
+            {
+                float2 w1 = twr[0];
+                asm volatile("" : "+f"(w1.x), "+f"(w1.y));  // keeps the chain inside the row loop (see row_fft)
+                float2 w = twr[4];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    float2 val = v[brev<32>(r)];
+                    if (r > 0) {
+                        val = cmul(val, w);
+                        if (r + 1 < 32) w = ((r + 1) % 8 == 0) ? twr[(r + 1) / 8] : cmul(w, w1);
+                    } else {
+                        val = __fmul2_rn(val, sg2);
+                    }
+                    tile[PL::at(r, t)] = val;
+                    if (r % 4 == 3) asm volatile("" ::: "memory");
+                }
+            }
+            team_sync<PL>(team);
+            // every warp of the team is past the previous antenna: its channel row may be replaced
+            if (t == 0) {
+                mbar_expect_tx(&bar_h[team], ROW_BYTES);
+                bulk_g2s(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team]);
+            }
+            // ---- stage 2 operands; the last warp to have read its own fetches the next antenna row into the tile
+            sh_stage2_read<PL>(v, tile, k1, q);
+            if (x_tma) {
+                __syncwarp();
+                if (lane == 0) {
+                    if (atomicAdd(&s_readers[team], 1u) == (unsigned)WPT - 1u) {
+                        s_readers[team] = 0u;
+                        if (a + 1 < p.n_ant) {
+                            fence_proxy_async();
+                            mbar_expect_tx(&bar_x[team], ROW_BYTES);
+                            bulk_g2s(tile, x_row + p.ant_stride, ROW_BYTES, &bar_x[team]);
+                        }
+                    }
+                }
+            } else {
+                team_sync<PL>(team);  // (plain-load fallback: the next row's stage 1 overwrites the tile)
+            }
+            fft_reg<32>(v);
+            // ---- twiddle W_T^(q*k2), radix-SH across the lanes, multiply-accumulate with conj(H)
+            constexpr int JB = kShBatch;
+            const float2* twq = s_tw2 + q;
+            mbar_wait(&bar_h[team], h_phase);
+            h_phase ^= 1u;
+#pragma unroll
+            for (int c = 0; c < 16 / JB; ++c) {
+                float2 tw[2 * JB], h[2 * JB];
+                sh_load_twiddles<SH, JB>(tw, twq, hi, c);
+#pragma unroll
+                for (int i = 0; i < 2 * JB; ++i) h[i] = lds_volatile(hbuf + (2 * JB * c + i) * T + t);
+                asm volatile("" ::: "memory");
+                float2 keep[JB], send[JB], A[JB], B[JB];
+#pragma unroll
+                for (int i = 0; i < JB; ++i) {
+                    keep[i] = cmul(v[2 * (JB * c + i)], tw[2 * i]);
+                    send[i] = cmul(v[2 * (JB * c + i) + 1], tw[2 * i + 1]);
+                }
+                sh_radix_batch<SH, JB>(keep, send, q, A, B);
+                // cpuLS.hpp:187-208: acc += Y * Hconj (both carry the slot's unit factor: it cancels)
+#pragma unroll
+                for (int i = 0; i < JB; ++i) {
+                    const int sl = 2 * (JB * c + i);
+                    acc[sl] = cmac(acc[sl], h[2 * i], A[i]);
+                    acc[sl + 1] = cmac(acc[sl + 1], h[2 * i + 1], B[i]);
+                }
+            }
+        }
+        team_sync<PL>(team);  // every warp is done with the last row before the tile becomes the demap byte buffer
+        mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(tile), valid, t, team);
+        team_sync<PL>(team);  // the byte buffer aliases the tile the next item's first row is copied into
     }
 }
 
