@@ -134,11 +134,18 @@ void fill_twiddles_impl(float2* tw)
             const double sg = (PL::SH == 2 && (t & 3) == 3) || (PL::SH == 4 && (t & 6) == 6) ? -1.0 : 1.0;
             tw[(k1 - 1) * PL::T + t] = make_float2((float)(sg * cos(ang)), (float)(sg * sin(ang)));
         }
-    if (PL::SH > 1)  // W_T^(q*k2) at [k2][q], k2 = 0..31 (row 0 is all ones: which lanes need it depends on the lane)
-        for (int k2 = 0; k2 < 32; ++k2)
+    if (PL::SH > 1)  // W_T^(q*k2) per lane position q: [16 register pairs j][SH] x (register 2j, register 2j+1), see sh_load_twiddles
+        for (int j = 0; j < 16; ++j)
             for (int q = 0; q < PL::SH; ++q) {
-                const double ang = -two_pi * (double)((q * k2) % PL::T) / (double)PL::T;
-                tw[PL::TW1 + k2 * PL::SH + q] = make_float2((float)cos(ang), (float)sin(ang));
+                const int hi = PL::SH == 2 ? q : (q >> 1);
+                int kk = 0;  // 5-bit reversal of 2j
+                for (int b = 0; b < 5; ++b)
+                    if ((2 * j) & (1 << b)) kk |= 1 << (4 - b);
+                for (int c = 0; c < 2; ++c) {
+                    const int k2 = kk + 16 * (hi ^ c);
+                    const double ang = -two_pi * (double)((q * k2) % PL::T) / (double)PL::T;
+                    tw[PL::TW1 + (j * PL::SH + q) * 2 + c] = make_float2((float)cos(ang), (float)sin(ang));
+                }
             }
     if (PL::R3 > 1)
         for (int k2 = 1; k2 < PL::R2; ++k2)
@@ -153,9 +160,9 @@ void fill_twiddles_impl(float2* tw)
 template <class PL, int MINB>
 constexpr int pilot_minb() { return (PL::P >= 32 && MINB > 2) ? 2 : MINB; }
 
-// dynamic shared memory of lsmrc_data_sh: W_T^(q*k2) table, per team one channel row and a tile
+// dynamic shared memory of lsmrc_data_sh: per team one channel row and a tile
 template <class PL>
-constexpr size_t data_sh_smem() { return sizeof(float2) * (size_t)(PL::TW2 + PL::TEAMS * (PL::N + PL::TILE)); }
+constexpr size_t data_sh_smem() { return sizeof(float2) * (size_t)(PL::TEAMS * (PL::N + PL::TILE)); }
 
 template <class PL, int MINB>
 cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
@@ -183,7 +190,12 @@ cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&generic, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS, PL::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_data_sh<PL, MINB>, PL::THREADS, data_sh_smem<PL>());
-        if (e == cudaSuccess && generic < *data_ctas_per_sm) *data_ctas_per_sm = generic;
+        if (e != cudaSuccess) return e;
+        // The occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
+        // columns); this one takes 128 of the SM's 512 per CTA, so registers and shared memory decide, as for the
+        // generic kernel of the same plan.
+        if (*data_ctas_per_sm < generic) *data_ctas_per_sm = generic < 4 ? generic : 4;
+        if (generic < *data_ctas_per_sm) *data_ctas_per_sm = generic;
         return e;
     }
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS,

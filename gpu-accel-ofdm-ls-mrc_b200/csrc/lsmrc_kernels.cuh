@@ -48,6 +48,9 @@
 #ifndef LSMRC_SH_XMODE
 #define LSMRC_SH_XMODE 1
 #endif
+#ifndef LSMRC_SH_HMODE  // channel rows staged in shared memory by bulk copy (1) or loaded straight from L2 (0)
+#define LSMRC_SH_HMODE 1
+#endif
 constexpr int kHStages = 3;  // depth of the Hconj ring (rows)
 constexpr int kTwChunk = 4;  // inter-stage twiddles fetched this many at a time, one chunk ahead of their use
 
@@ -309,6 +312,60 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) ones
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- tensor memory as a per-thread constant store --------------------------------------------------------
+// The FFT twiddles of a thread are the same for every row it transforms, but 31 + 32 complex values do not fit in
+// the register file next to the FFT working set and the MRC accumulators, so the kernels used to re-read them from a
+// shared-memory table (or regenerate them by a recurrence) for every row -- on the very pipes that bound them.
+// Blackwell's tensor memory is a third on-chip store with its own data path: 128 lanes x 512 32-bit columns per SM,
+// lane 32*(warp % 4) + l private to thread l of the warp when accessed with the 32x32b shape.  Measured on B200
+// (tools/ubench_tmem.cu, profiles/r02_ubench_tmem.txt): next to a saturated shared-memory port, fetching 16 complex
+// constants per row costs +24 % from shared memory and +1.5 % from tensor memory.
+// Each CTA (exactly 4 warps) allocates kTmemCols columns once and frees them at exit.
+__device__ __forceinline__ uint32_t tmem_alloc_cols(uint32_t* s_slot, int n_cols_pow2, int warp)
+{
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_slot)), "r"(n_cols_pow2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *s_slot + (((uint32_t)(warp & 3) * 32u) << 16);  // this warp's lane quarter
+}
+__device__ __forceinline__ void tmem_free_cols(uint32_t base, int n_cols_pow2, int warp)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(n_cols_pow2) : "memory");
+}
+// 4 complex values -> columns [col, col + 8) of the calling thread's lane
+__device__ __forceinline__ void tmem_store4(uint32_t taddr, int col, const float2 (&v)[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr + (uint32_t)col),
+                 "r"(__float_as_uint(v[0].x)), "r"(__float_as_uint(v[0].y)), "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)),
+                 "r"(__float_as_uint(v[2].x)), "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 8 complex values <- columns [col, col + 16); returns after the load has landed (the registers pass through the
+// wait so that no use can be scheduled ahead of it)
+__device__ __forceinline__ void tmem_load8(uint32_t taddr, int col, float2 (&v)[8])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr + (uint32_t)col));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+}
+
 template <class PL>
 __device__ __forceinline__ void team_sync(int team)
 {
@@ -456,14 +513,19 @@ __device__ __forceinline__ void sh_radix_batch(const float2 (&keep)[JB], const f
 
 constexpr int kShBatch = 4;  // register pairs per shuffle batch (= one 8-slot chunk of the Hconj ring)
 
-// twiddles W_T^(q*k2) of the 2*JB registers of batch jb: register r holds k2 = brev(r & ~1) + 16*(hi ^ (r & 1))
+// twiddles W_T^(q*k2) of the 2*JB registers of batch jb.  Register r of lane position q holds k2 = brev(r & ~1) +
+// 16*(hi ^ (r & 1)), hi = the high bit of q; the table is laid out per lane position, [16 register pairs][SH] entries of
+// (twiddle of register 2j, twiddle of register 2j+1), so a pair is ONE 128-bit load whose SH distinct addresses per
+// warp are broadcast (one shared-memory wavefront instead of four for two 64-bit loads).  twq = table + 2*q.
 template <int SH, int JB>
-__device__ __forceinline__ void sh_load_twiddles(float2 (&tw)[2 * JB], const float2* twq, int hi, int jb)
+__device__ __forceinline__ void sh_load_twiddles(float2 (&tw)[2 * JB], const float2* twq, int jb)
 {
 #pragma unroll
-    for (int i = 0; i < 2 * JB; ++i) {
-        const int r = 2 * JB * jb + i;
-        tw[i] = lds_volatile(twq + (brev<32>(r & ~1) + 16 * (hi ^ (r & 1))) * SH);
+    for (int i = 0; i < JB; ++i) {
+        const float2* src = twq + (JB * jb + i) * SH * 2;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(tw[2 * i].x), "=f"(tw[2 * i].y), "=f"(tw[2 * i + 1].x), "=f"(tw[2 * i + 1].y)
+                     : "r"(smem_u32(src)));
     }
 }
 
@@ -567,19 +629,18 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
         const int lane = t & 31;
         const int q = lane % SH;
         const int k1 = lane / SH + (32 / SH) * (t >> 5);
-        const int hi = (SH == 2) ? q : (q >> 1);
         float2 u[32];
         sh_stage2_read<PL>(u, tile, k1, q);
         after_reads();  // the tile is free from here on
         fft_reg<32>(u);
         // twiddles W_T^(q*k2), fetched one batch ahead of their multiplies; then the cross-lane radix-SH stage
         constexpr int JB = kShBatch;
-        const float2* twq = s_tw2 + q;
+        const float2* twq = s_tw2 + 2 * q;
         float2 tw[2 * JB], twn[2 * JB];
-        sh_load_twiddles<SH, JB>(tw, twq, hi, 0);
+        sh_load_twiddles<SH, JB>(tw, twq, 0);
 #pragma unroll
         for (int jb = 0; jb < 16 / JB; ++jb) {
-            if (jb + 1 < 16 / JB) sh_load_twiddles<SH, JB>(twn, twq, hi, jb + 1);
+            if (jb + 1 < 16 / JB) sh_load_twiddles<SH, JB>(twn, twq, jb + 1);
             asm volatile("" ::: "memory");
             float2 keep[JB], send[JB], A[JB], B[JB];
 #pragma unroll
@@ -1282,7 +1343,9 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
 //    values -- and is needed only after the stage-2 transform.
 // Neither the samples nor the channel values are waited for on the scoreboard (35 % of all stall samples of the
 // round-1 kernels, profiles/r02_before_ncu_c4.txt), and a row costs one team barrier instead of three.
-// Shared memory per CTA: W_T^(q*k2) table + TEAMS x (channel row N + tile N) complex = 65 KB -> 3 CTAs per SM.
+//  * the twiddles of both stages are per-thread constants; they live in tensor memory (see tmem_load8) and cost
+//    neither shared-memory wavefronts (a table) nor fp32 instructions (a recurrence).
+// Shared memory per CTA: TEAMS x (channel row N + tile N) complex = 64 KB -> 3 CTAs per SM.
 // Rows that are not 16-byte aligned (odd prefix lengths) are read with plain 64-bit loads instead of bulk copies.
 template <class PL, int MINB>
 __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelParams p)
@@ -1290,10 +1353,9 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
     constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, ROW = PL::ROW, TEAMS = PL::TEAMS;
     constexpr int WPT = T / 32;  // warps per team
     constexpr uint32_t ROW_BYTES = N * sizeof(float2);
-    static_assert(SH > 1 && PL::TW_REC && ROW == T, "shuffle-stage plans only");
+    static_assert(SH > 1 && ROW == T, "shuffle-stage plans only");
     extern __shared__ __align__(16) float2 smem[];
-    float2* s_tw2 = smem;                   // [32][SH]
-    float2* s_h = smem + PL::TW2;           // [TEAMS][N]   conj(H) of the current antenna, slot-major
+    float2* s_h = smem;                     // [TEAMS][N]   conj(H) of the current antenna, slot-major
     float2* s_tiles = s_h + TEAMS * N;      // [TEAMS][32][T]
     __shared__ __align__(8) uint64_t bar_x[TEAMS], bar_h[TEAMS];
     __shared__ unsigned int s_readers[TEAMS];  // warps of the team that have read their stage-2 operands of this row
@@ -1305,7 +1367,6 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
     float2* tile = s_tiles + team * N;
     float2* hbuf = s_h + team * N;
 
-    for (int i = threadIdx.x; i < PL::TW2; i += PL::THREADS) s_tw2[i] = p.twiddles[PL::TW1 + i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < TEAMS; ++i) {
             mbar_init(&bar_x[i], 1);
@@ -1314,19 +1375,38 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
         }
         mbar_fence_init();
     }
-    // stage-1 twiddle recurrence (see row_fft): step, three restart values, signed start
-    float2 twr[5];
-    twr[0] = p.twiddles[t];
-#pragma unroll
-    for (int a = 1; a < 4; ++a) twr[a] = p.twiddles[(8 * a - 1) * T + t];
-    twr[4] = twr[0];
-    const float sg = PL::stage1_sign(t);
-    twr[0] = make_float2(sg * twr[0].x, sg * twr[0].y);
-    const float2 sg2 = make_float2(sg, sg);
     // this thread's stage-2 role: row k1 of the tile, lane position q of the shuffle group
     const int q = lane % SH;
-    const int hi = (SH == 2) ? q : (q >> 1);
     const int k1 = lane / SH + (32 / SH) * wt;
+    // Both twiddle sets of this thread go to its tensor-memory lane once: columns [0, 64) the 32 stage-1 factors
+    // stage1_sign(t) * W_N^(t*r) (r = 0: just the sign), columns [64, 128) the 32 factors W_T^(q*k2) of its stage-2
+    // registers (k2 as in sh_radix_batch).
+    static_assert(PL::THREADS == 128, "one tensor-memory lane per thread: CTAs of exactly four warps");
+    constexpr int kTmemCols = 128;
+    __shared__ uint32_t s_tmem;
+    const uint32_t tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+    {
+        const float sg = PL::stage1_sign(t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float2 w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 4 * c + i;
+                w[i] = (r == 0) ? make_float2(sg, 0.f) : p.twiddles[(r - 1) * T + t];  // (the table carries the sign)
+            }
+            tmem_store4(tmem, 8 * c, w);
+        }
+        const float2* tq = p.twiddles + PL::TW1 + 2 * q;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float2 w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = tq[((4 * c + i) / 2) * SH * 2 + ((4 * c + i) & 1)];
+            tmem_store4(tmem, 64 + 8 * c, w);
+        }
+        tmem_store_wait();
+    }
     __syncthreads();
 
     const long long n_work = (long long)p.n_frames * p.n_sym_work;
@@ -1381,29 +1461,24 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
             }
             // ---- stage 1: 32-point transform over n1, twiddle W_N^(t*k1) by recurrence, into the swizzled tile
             fft_reg<32>(v);
-            {
-                float2 w1 = twr[0];
-                asm volatile("" : "+f"(w1.x), "+f"(w1.y));  // keeps the chain inside the row loop (see row_fft)
-                float2 w = twr[4];
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    float2 val = v[brev<32>(r)];
-                    if (r > 0) {
-                        val = cmul(val, w);
-                        if (r + 1 < 32) w = ((r + 1) % 8 == 0) ? twr[(r + 1) / 8] : cmul(w, w1);
-                    } else {
-                        val = __fmul2_rn(val, sg2);
-                    }
-                    tile[PL::at(r, t)] = val;
-                    if (r % 4 == 3) asm volatile("" ::: "memory");
+            for (int c = 0; c < 4; ++c) {
+                float2 w[8];
+                tmem_load8(tmem, 16 * c, w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 8 * c + i;
+                    tile[PL::at(r, t)] = cmul(v[brev<32>(r)], w[i]);
                 }
             }
             team_sync<PL>(team);
             // every warp of the team is past the previous antenna: its channel row may be replaced
+#if LSMRC_SH_HMODE
             if (t == 0) {
                 mbar_expect_tx(&bar_h[team], ROW_BYTES);
                 bulk_g2s(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team]);
             }
+#endif
             // ---- stage 2 operands; the last warp to have read its own fetches the next antenna row into the tile
             sh_stage2_read<PL>(v, tile, k1, q);
             if (x_tma) {
@@ -1424,15 +1499,23 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
             fft_reg<32>(v);
             // ---- twiddle W_T^(q*k2), radix-SH across the lanes, multiply-accumulate with conj(H)
             constexpr int JB = kShBatch;
-            const float2* twq = s_tw2 + q;
+#if LSMRC_SH_HMODE
             mbar_wait(&bar_h[team], h_phase);
             h_phase ^= 1u;
+#else
+            const float2* hw_row = hw_frame + (long long)a * N + t;
+#endif
 #pragma unroll
             for (int c = 0; c < 16 / JB; ++c) {
                 float2 tw[2 * JB], h[2 * JB];
-                sh_load_twiddles<SH, JB>(tw, twq, hi, c);
+                tmem_load8(tmem, 64 + 16 * c, tw);
+#if LSMRC_SH_HMODE
 #pragma unroll
                 for (int i = 0; i < 2 * JB; ++i) h[i] = lds_volatile(hbuf + (2 * JB * c + i) * T + t);
+#else
+#pragma unroll
+                for (int i = 0; i < 2 * JB; ++i) h[i] = __ldg(hw_row + (2 * JB * c + i) * T);
+#endif
                 asm volatile("" ::: "memory");
                 float2 keep[JB], send[JB], A[JB], B[JB];
 #pragma unroll
@@ -1454,6 +1537,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
         mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(tile), valid, t, team);
         team_sync<PL>(team);  // the byte buffer aliases the tile the next item's first row is copied into
     }
+    tmem_free_cols(s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
 }
 
 // ---- stand-alone per-step kernels: the individually callable steps of gpuLS.cuh:87-99 -----------
