@@ -164,6 +164,33 @@ constexpr int pilot_minb() { return (PL::P >= 32 && MINB > 2) ? 2 : MINB; }
 template <class PL>
 constexpr size_t data_sh_smem() { return sizeof(float2) * (size_t)(PL::TEAMS * (PL::N + PL::TILE)); }
 
+// Resident CTAs per SM of a kernel that allocates `tmem_cols` tensor-memory columns per CTA.  The runtime's occupancy
+// calculator answers 1 for any such kernel (it cannot know how many of the SM's 512 columns a CTA takes), so the
+// limits are applied by hand: registers (allocated per warp in units of 256), shared memory (dynamic + static + 1 KB
+// reserved per CTA), warps, and columns.
+template <class K>
+cudaError_t occupancy_with_tmem(int* ctas_per_sm, K kernel, int threads, size_t dyn_smem, int tmem_cols)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    int regs_sm = 0, smem_sm = 0, threads_sm = 0;
+    if ((e = cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&threads_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev)) != cudaSuccess) return e;
+    const int warps = (threads + 31) / 32;
+    const int regs_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+    int n = regs_sm / (regs_warp * warps);
+    const size_t smem_cta = dyn_smem + fa.sharedSizeBytes + 1024;
+    if ((int)((size_t)smem_sm / smem_cta) < n) n = (int)((size_t)smem_sm / smem_cta);
+    if (threads_sm / threads < n) n = threads_sm / threads;
+    if (tmem_cols > 0 && 512 / tmem_cols < n) n = 512 / tmem_cols;
+    *ctas_per_sm = n;
+    return cudaSuccess;
+}
+
 template <class PL, int MINB>
 cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
 {
@@ -181,25 +208,20 @@ cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(pilot_ctas_per_sm, lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()>,
                                                       PL::THREADS, PL::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    // (tensor-memory columns per CTA: 2P for the stage-1 twiddles, power of two >= 32)
+    e = occupancy_with_tmem(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS, PL::SMEM_BYTES, PL::TW_TMEM ? 2 * PL::P : 0);
+    if (e != cudaSuccess) return e;
     if constexpr (PL::SH > 1) {
         // shuffle-stage plans: large batches run the dedicated data kernel (the generic one serves the antenna-split
         // launches of tiny batches); both share the persistent grid size
         e = cudaFuncSetAttribute(lsmrc_data_sh<PL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)data_sh_smem<PL>());
         if (e != cudaSuccess) return e;
-        int generic = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&generic, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS, PL::SMEM_BYTES);
+        int sh = 0;
+        e = occupancy_with_tmem(&sh, lsmrc_data_sh<PL, MINB>, PL::THREADS, data_sh_smem<PL>(), 128);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_data_sh<PL, MINB>, PL::THREADS, data_sh_smem<PL>());
-        if (e != cudaSuccess) return e;
-        // The occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many
-        // columns); this one takes 128 of the SM's 512 per CTA, so registers and shared memory decide, as for the
-        // generic kernel of the same plan.
-        if (*data_ctas_per_sm < generic) *data_ctas_per_sm = generic < 4 ? generic : 4;
-        if (generic < *data_ctas_per_sm) *data_ctas_per_sm = generic;
-        return e;
+        if (sh < *data_ctas_per_sm) *data_ctas_per_sm = sh;
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS,
-                                                         PL::SMEM_BYTES);
+    return cudaSuccess;
 }
 
 template <class PL, int MINB>
@@ -303,23 +325,15 @@ PlanOps make_ops()
 
 // ---- the plans.  Template arguments: N, P (points per thread), R2, R3, teams per CTA, tile buffers per team, rows of
 // x prefetched to L2, rows of Hconj prefetched to L1, register prefetch of the next row, x through L1, Hconj ring,
-// x rows by bulk copy, stage-1 twiddles by recurrence, lanes of the shuffle stage.  Each setting is the measured
+// x rows by bulk copy, stage-1 twiddles in tensor memory, lanes of the shuffle stage.  Each setting is the measured
 // winner of its A/B (DESIGN.md section 3 keeps the log, including the variants that lost and were deleted).
 using Plan64 = Plan<64, 16, 4, 1, 32, 2, 0, 0, 1>;
 using Plan128 = Plan<128, 16, 8, 1, 16, 2, 0, 0, 1>;
 using Plan256 = Plan<256, 16, 16, 1, 8, 2, 0, 1, 1>;
-using Plan512 = Plan<512, 32, 16, 1, 8, 1, 1, 1>;
-using Plan1024 = Plan<1024, 32, 32, 1, 4, 1, 0, 1, 0, false, true, true>;
-#ifndef LSMRC_SHUFFLE_PLANS  // development A/B switch: 0 = the round-1 three-stage plans for 2048/4096 points
-#define LSMRC_SHUFFLE_PLANS 1
-#endif
-#if LSMRC_SHUFFLE_PLANS
+using Plan512 = Plan<512, 32, 16, 1, 8, 1, 1, 1>;  // (tensor-memory twiddles measured 10 % slower here: teams of 16 threads)
+using Plan1024 = Plan<1024, 32, 32, 1, 4, 1, 0, 1, 0, false, true, true, true>;
 using Plan2048 = Plan<2048, 32, 32, 1, 2, 1, 1, 0, 0, false, false, false, true, 2>;
 using Plan4096 = Plan<4096, 32, 32, 1, 1, 1, 1, 0, 0, false, false, false, true, 4>;
-#else
-using Plan2048 = Plan<2048, 32, 16, 4, 2, 1, 1, 0, 0, false, false, false, true>;
-using Plan4096 = Plan<4096, 32, 32, 4, 1, 1, 1, 0, 0, false, false, false, true>;
-#endif
 constexpr int kMinBlocks = 3;  // 3 CTAs (12 warps) per SM at 168 registers: measured best for every size
 
 // LSMRC_ONLY_N=<size> (development): instantiate the kernels of one FFT size only -- a full build takes 85 s
@@ -364,19 +378,7 @@ const PlanOps* find_plan(int N)
 // channel rows are in bin order: the shuffle-stage plans need the pilot kernel to share their slot layout.
 const PilotOps* find_pilot_plan(int N)
 {
-#if !LSMRC_SHUFFLE_PLANS
-    static const PilotOps plans[] = {
-#if LSMRC_HAVE(2048)
-        make_pilot_ops<Plan<2048, 16, 16, 8, 2, 1, 1, 0>, 2>(),
-#endif
-#if LSMRC_HAVE(4096)
-        make_pilot_ops<Plan<4096, 16, 16, 16, 1, 1, 1, 0>, 2>(),
-#endif
-    };
-    for (const PilotOps& o : plans)
-        if (o.N == N) return &o;
-#endif
-    (void)N;
+    (void)N;  // (none at present: the plans whose pilot kernel had its own are now shuffle-stage plans)
     return nullptr;
 }
 

@@ -112,7 +112,7 @@ struct KernelParams {
 };
 
 template <int N_, int P_, int R2_, int R3_, int TEAMS_, int NBUF_ = 2, int PF_X_ = 0, int PF_H_ = 0, int REG_PF_ = 0, bool X_L1_ = false, bool H_RING_ = false,
-          bool X_TMA_ = false, bool TW_REC_ = false, int SH_ = 1>
+          bool X_TMA_ = false, bool TW_TMEM_ = false, int SH_ = 1>
 struct Plan {
     // SH > 1 (2 or 4; N = 32 * 32 * SH, teams of SH warps): the LAST radix-SH stage runs across the SH adjacent lanes
     // of a warp through shuffles instead of a second shared-memory exchange (see row_fft).  Measured on B200
@@ -126,12 +126,11 @@ struct Plan {
     //    only exported values (Hconj in the reference layout, the stand-alone FFT) are corrected.
     static constexpr int SH = SH_;
     static_assert(SH_ == 1 || ((SH_ == 2 || SH_ == 4) && P_ == 32 && R2_ == 32 && R3_ == 1), "shuffle stage: N = 32*32*SH");
-    // TW_REC (data kernel, P = 32): the inter-stage twiddles W^(t*k1) are not read from the shared-memory table but
-    // generated in registers by the recurrence w(k1+1) = w(k1) * W^t, restarted from exact table values every 8
-    // steps (4 register pairs for the whole kernel, one extra complex multiply per twiddle, <= 7 accumulated
-    // roundings).  Pays where the shared-memory/LSU pipe is the limit (the three-stage plans); neutral for N = 1024.
-    static constexpr bool TW_REC = TW_REC_;
-    static_assert(!TW_REC_ || P_ == 32, "TW_REC is written for 32 points per thread");
+    // TW_TMEM (data kernel, 32 points per thread, CTAs of four warps): the inter-stage twiddles W_N^(t*k1) of a
+    // thread are not re-read from the shared-memory table for every row but kept in the thread's tensor-memory lane
+    // (see tmem_load8): 31 fewer 64-bit shared loads per thread and row on the pipe that bounds these kernels.
+    static constexpr bool TW_TMEM = TW_TMEM_;
+    static_assert(!TW_TMEM_ || (P_ == 32 && (N_ / P_) * TEAMS_ == 128), "TW_TMEM: 32 points per thread, four warps per CTA");
     // X_TMA (teams of whole warps): the data kernel brings each antenna row into the team's tile with one bulk
     // async copy (TMA), issued while the previous row is still in its last-stage arithmetic, instead of 64-bit
     // loads into registers at the top of the row.  The copy lays the row out linearly over the first N
@@ -546,6 +545,23 @@ __device__ __forceinline__ void sh_stage2_read(float2 (&u)[32], const float2* __
     }
 }
 
+// writes the P stage-1 factors of thread t (k1 = 0: the bare sign, else the signed table entry) to columns [0, 2P)
+template <class PL>
+__device__ __forceinline__ void tmem_fill_stage1(uint32_t tmem, const float2* __restrict__ table, int t)
+{
+    const float sg = PL::stage1_sign(t);
+#pragma unroll
+    for (int c = 0; c < PL::P / 4; ++c) {
+        float2 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = 4 * c + i;
+            w[i] = (r == 0) ? make_float2(sg, 0.f) : table[(r - 1) * PL::T + t];  // (the table carries the sign)
+        }
+        tmem_store4(tmem, 8 * c, w);
+    }
+}
+
 struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
@@ -556,31 +572,24 @@ template <class PL, class Sink, class Hook = NoHook>
 __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __restrict__ x_next,
                                         float2* __restrict__ tile, const float2* __restrict__ s_tw1,
                                         const float2* __restrict__ s_tw2, int t, int team, Sink&& sink,
-                                        const float2* tw_regs = nullptr, Hook&& after_reads = Hook())
+                                        uint32_t tmem_tw = 0, Hook&& after_reads = Hook())
 {
     constexpr int P = PL::P, T = PL::T, ROW = PL::ROW, R2 = PL::R2, R3 = PL::R3;
     fft_reg<P>(v);
-    if (PL::TW_REC && tw_regs != nullptr) {
-        // tw_regs[0] = W^t; tw_regs[1..3] = exact W^(8t), W^(16t), W^(24t).  The step is laundered through an empty
-        // asm: the chain depends on kernel-lifetime values only, and left visible the compiler hoists all 31
-        // products out of the row loop and spills them.
-        // Shuffle-stage plans: every stage-1 output of this thread carries the sign stage1_sign(t) (see Plan); the
-        // restart values tw_regs[1..3] and the chain's start tw_regs[4] have it folded in, the step tw_regs[0] has not.
-        float2 w1 = tw_regs[0];
-        asm volatile("" : "+f"(w1.x), "+f"(w1.y));
-        float2 w = (PL::SH > 1) ? tw_regs[4] : w1;
+    if (PL::TW_TMEM && tmem_tw != 0) {
+        // inter-stage twiddles from the thread's tensor-memory lane: columns [0, 2P) hold stage1_sign(t) * W_N^(t*k1),
+        // k1 = 0..P-1 (entry 0 is the bare sign), written once per kernel by tmem_fill_stage1
 #pragma unroll
-        for (int k1 = 0; k1 < P; ++k1) {
-            float2 val = v[brev<P>(k1)];
-            if (k1 > 0) {
-                val = cmul(val, w);
-                if (k1 + 1 < P) w = ((k1 + 1) % 8 == 0) ? tw_regs[(k1 + 1) / 8] : cmul(w, w1);
-            } else if (PL::SH > 1) {
-                const float sg = PL::stage1_sign(t);
-                val = __fmul2_rn(val, make_float2(sg, sg));
+        for (int c = 0; c < P / 8; ++c) {
+            float2 w[8];
+            tmem_load8(tmem_tw, 16 * c, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k1 = 8 * c + i;
+                float2 val = v[brev<P>(k1)];
+                if (k1 > 0 || PL::SH > 1) val = cmul(val, w[i]);
+                tile[PL::at(k1, t)] = val;
             }
-            tile[PL::at(k1, t)] = val;
-            if (k1 % 4 == 3) asm volatile("" ::: "memory");  // keep the twiddle chain from running ahead of its use
         }
     } else {
     // Inter-stage twiddles W_N^(t*k1) come from the shared table.  They are fetched in chunks of
@@ -1168,17 +1177,13 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
             bulk_g2s(s_hring + sr * N, src_row, ROW_BYTES, &bar_full[sr]);
         };
 
-        float2 twr[PL::TW_REC ? 5 : 1];
-        if constexpr (PL::TW_REC) {
-            twr[0] = s_tw1[t];
-#pragma unroll
-            for (int a = 1; a < 4; ++a) twr[a] = s_tw1[(8 * a - 1) * T + t];
-            // shuffle-stage plans: the table carries stage1_sign(t); the recurrence's step must not
-            twr[4] = twr[0];
-            if constexpr (PL::SH > 1) {
-                const float sg = PL::stage1_sign(t);
-                twr[0] = make_float2(sg * twr[0].x, sg * twr[0].y);
-            }
+        __shared__ uint32_t s_tmem;
+        uint32_t tmem = 0;
+        constexpr int kTmemCols = 2 * P;
+        if constexpr (PL::TW_TMEM) {
+            tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+            tmem_fill_stage1<PL>(tmem, p.twiddles, t);
+            tmem_store_wait();
         }
         __shared__ int s_item;
         for (;;) {
@@ -1285,7 +1290,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
                                 if (a_ok) acc[sl] = cmac(acc[sl], h, y);
                             }
                         },
-                        PL::TW_REC ? twr : nullptr,
+                        tmem,
                         [&]() {
                             if constexpr (PL::X_TMA) {
                                 // the tile has been read for the last time in this row: fetch the next row
@@ -1326,6 +1331,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(my_tiles), valid, t, team);
         team_sync<PL>(team);  // the byte buffer aliases the tile the next item writes
         }  // work items
+        if constexpr (PL::TW_TMEM) tmem_free_cols(s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
     }
 }
 
@@ -1386,17 +1392,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
     __shared__ uint32_t s_tmem;
     const uint32_t tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
     {
-        const float sg = PL::stage1_sign(t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float2 w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = 4 * c + i;
-                w[i] = (r == 0) ? make_float2(sg, 0.f) : p.twiddles[(r - 1) * T + t];  // (the table carries the sign)
-            }
-            tmem_store4(tmem, 8 * c, w);
-        }
+        tmem_fill_stage1<PL>(tmem, p.twiddles, t);
         const float2* tq = p.twiddles + PL::TW1 + 2 * q;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
