@@ -191,6 +191,10 @@ cudaError_t occupancy_with_tmem(int* ctas_per_sm, K kernel, int threads, size_t 
     return cudaSuccess;
 }
 
+// dynamic shared memory of lsmrc_pilot_sh: the LS-divide table (one row) and a tile per team
+template <class PL>
+constexpr size_t pilot_sh_smem() { return sizeof(float2) * (size_t)(PL::N + PL::TEAMS * PL::TILE); }
+
 template <class PL, int MINB>
 cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
 {
@@ -220,6 +224,11 @@ cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
         e = occupancy_with_tmem(&sh, lsmrc_data_sh<PL, MINB>, PL::THREADS, data_sh_smem<PL>(), 128);
         if (e != cudaSuccess) return e;
         if (sh < *data_ctas_per_sm) *data_ctas_per_sm = sh;
+        // ... and the dedicated pilot kernel (batches with one antenna group per frame or more)
+        e = cudaFuncSetAttribute(lsmrc_pilot_sh<PL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pilot_sh_smem<PL>());
+        if (e != cudaSuccess) return e;
+        e = occupancy_with_tmem(pilot_ctas_per_sm, lsmrc_pilot_sh<PL, MINB>, PL::THREADS, pilot_sh_smem<PL>(), 128);
+        if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
@@ -236,6 +245,14 @@ cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int ma
         const long long n_virtual = (long long)((p.n_frames + p.frames_per_cta - 1) / p.frames_per_cta) * p.n_groups;
         const long long cap = p.pilot_grid_cap > 0 ? p.pilot_grid_cap : n_virtual;
         const unsigned grid = (unsigned)(n_virtual < cap ? n_virtual : cap);  // CTAs stride over the virtual CTAs
+#ifndef LSMRC_NO_PILOT_SH
+        if constexpr (PL::SH > 1) {
+            if (p.frames_per_cta == 1) {
+                lsmrc_pilot_sh<PL, MINB><<<grid, PL::THREADS, pilot_sh_smem<PL>(), st>>>(p);
+                return cudaGetLastError();
+            }
+        }
+#endif
         lsmrc_kernel<PL, MODE_PILOT, pilot_minb<PL, MINB>()><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(p);
     } else {
         long long items;
@@ -623,6 +640,9 @@ int launch_pilot(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, f
     }
     p.epart = ch.epart;
     p.counters = ch.counters;
+    // bulk async copies of antenna rows need 16-byte aligned rows: even strides and prefix, aligned base
+    p.x_tma = (reinterpret_cast<uintptr_t>(p.rx) % 16 == 0) && p.cp % 2 == 0 && p.ant_stride % 2 == 0 && p.sym_stride % 2 == 0 &&
+              p.frame_stride % 2 == 0;
     {
         // tiny virtual CTAs (a round or two of row FFTs per team: few antennas, small N) amortise the per-CTA setup by
         // striding one resident wave of CTAs over them; larger ones are left to the hardware scheduler, which

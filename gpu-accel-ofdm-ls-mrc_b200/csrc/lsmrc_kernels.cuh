@@ -294,8 +294,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait may put the warp to sleep until the phase completes.  ptxas hoists the first probe of a wait loop far up
+// into the arithmetic ahead of it (seen in SASS: into the middle of the preceding transform), where a sleeping probe
+// stalls work that does not depend on the barrier at all -- so the first probe is the non-blocking test_wait, and
+// the sleeping form is only used inside the loop, which stays where the program has it.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+    if (mbar_test_wait(bar, parity)) return;
     while (!mbar_try_wait(bar, parity)) {
     }
 }
@@ -560,6 +579,21 @@ __device__ __forceinline__ void tmem_fill_stage1(uint32_t tmem, const float2* __
         }
         tmem_store4(tmem, 8 * c, w);
     }
+}
+
+// Zero-instruction scheduling fence for register values: everything v[] depends on is computed before this point and
+// nothing that uses v[] afterwards is started ahead of it.  Used to keep arithmetic on the near side of a wait (the
+// compiler may move plain arithmetic across a volatile asm, e.g. sink a transform below an mbarrier wait and so
+// shorten the time the awaited copy has to land).
+template <int NV>
+__device__ __forceinline__ void pin_values(float2 (&v)[NV])
+{
+    static_assert(NV % 8 == 0, "groups of eight");
+#pragma unroll
+    for (int i = 0; i < NV; i += 8)
+        asm volatile("" : "+f"(v[i].x), "+f"(v[i].y), "+f"(v[i + 1].x), "+f"(v[i + 1].y), "+f"(v[i + 2].x), "+f"(v[i + 2].y), "+f"(v[i + 3].x),
+                          "+f"(v[i + 3].y), "+f"(v[i + 4].x), "+f"(v[i + 4].y), "+f"(v[i + 5].x), "+f"(v[i + 5].y), "+f"(v[i + 6].x),
+                          "+f"(v[i + 6].y), "+f"(v[i + 7].x), "+f"(v[i + 7].y));
 }
 
 struct NoHook {
@@ -1335,6 +1369,91 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
     }
 }
 
+// ---- row pipeline shared by the two kernels of the shuffle-stage plans -----------------------------------------
+// Per-team state of the pipeline in shared memory / tensor memory.
+template <class PL>
+struct ShRow {
+    float2* tile;            // [32][T] dense, columns swizzled (Plan::at)
+    uint64_t* bar_x;         // completes on the bytes of the antenna row in flight
+    unsigned int* readers;   // warps of the team that have read their stage-2 operands of the current row
+    uint32_t tmem;           // this thread's tensor-memory lane: columns [0,64) stage-1, [64,128) stage-2 twiddles
+    uint32_t x_phase;
+    bool x_tma;
+    int t, lane, wt, team, q, k1;
+};
+
+// request antenna row `x_row` into the team's tile (one bulk copy; the caller has made sure the tile is free)
+template <class PL>
+__device__ __forceinline__ void sh_fetch_row(const ShRow<PL>& r, const float2* x_row)
+{
+    fence_proxy_async();  // the tile's earlier generic-proxy accesses are ordered before the copy
+    mbar_expect_tx(r.bar_x, (uint32_t)(PL::N * sizeof(float2)));
+    bulk_g2s(r.tile, x_row, (uint32_t)(PL::N * sizeof(float2)), r.bar_x);
+}
+
+// Everything of a row up to the stage-2 transform: samples out of the tile (or by plain loads when rows are not
+// 16-byte aligned), stage 1 with the twiddles from tensor memory, the ONE team barrier of the row, stage-2 operands,
+// the request for the next row (x_next, may be nullptr) by whichever warp finishes its reads last, and the
+// 32-point stage-2 transform.  `after_barrier()` runs right behind the team barrier: passing it proves that every
+// warp of the team is done with the previous row.  On return v[r] holds register r of the stage-2 transform.
+template <class PL, class F>
+__device__ __forceinline__ void sh_row_front(ShRow<PL>& r, float2 (&v)[32], const float2* x_row, const float2* x_next, F&& after_barrier)
+{
+    constexpr int T = PL::T, WPT = T / 32;
+    if (r.x_tma) {
+        mbar_wait(r.bar_x, r.x_phase);
+        r.x_phase ^= 1u;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) v[n1] = r.tile[n1 * T + r.t];  // as the copy laid the row out: linear
+        __syncwarp();  // stage 1 writes into columns of this warp's lanes only
+    } else {
+        row_load<PL>(v, x_row, r.t);
+        if (x_next != nullptr) prefetch_row<T, false>(x_next, PL::N, r.t);
+    }
+    fft_reg<32>(v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2 w[8];
+        tmem_load8(r.tmem, 16 * c, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = 8 * c + i;
+            r.tile[PL::at(k, r.t)] = cmul(v[brev<32>(k)], w[i]);
+        }
+    }
+    team_sync<PL>(r.team);
+    after_barrier();
+    sh_stage2_read<PL>(v, r.tile, r.k1, r.q);
+    if (r.x_tma) {
+        __syncwarp();
+        if (r.lane == 0) {
+            if (atomicAdd(r.readers, 1u) == (unsigned)WPT - 1u) {
+                *r.readers = 0u;
+                if (x_next != nullptr) sh_fetch_row<PL>(r, x_next);
+            }
+        }
+    } else {
+        team_sync<PL>(r.team);  // (plain-load fallback: the next row's stage 1 overwrites the tile)
+    }
+    fft_reg<32>(v);
+}
+
+// twiddles of both stages of thread t into its tensor-memory lane (see lsmrc_data_sh)
+template <class PL>
+__device__ __forceinline__ void sh_fill_tmem(uint32_t tmem, const float2* __restrict__ table, int t, int q)
+{
+    tmem_fill_stage1<PL>(tmem, table, t);
+    const float2* tq = table + PL::TW1 + 2 * q;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float2 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = tq[((4 * c + i) / 2) * PL::SH * 2 + ((4 * c + i) & 1)];
+        tmem_store4(tmem, 64 + 8 * c, w);
+    }
+    tmem_store_wait();
+}
+
 // ---- data kernel of the shuffle-stage plans (2048 and 4096 points) --------------------------------------------
 // Same job as MODE_DATA above (persistent CTAs, one team per (frame, data symbol), antenna loop with the MRC sums in
 // registers), restructured around what the shuffle stage frees up:
@@ -1391,24 +1510,20 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
     constexpr int kTmemCols = 128;
     __shared__ uint32_t s_tmem;
     const uint32_t tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
-    {
-        tmem_fill_stage1<PL>(tmem, p.twiddles, t);
-        const float2* tq = p.twiddles + PL::TW1 + 2 * q;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float2 w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = tq[((4 * c + i) / 2) * SH * 2 + ((4 * c + i) & 1)];
-            tmem_store4(tmem, 64 + 8 * c, w);
-        }
-        tmem_store_wait();
-    }
+    sh_fill_tmem<PL>(tmem, p.twiddles, t, q);
     __syncthreads();
 
     const long long n_work = (long long)p.n_frames * p.n_sym_work;
     const int n_items = (int)((n_work + TEAMS - 1) / TEAMS);
-    const bool x_tma = p.x_tma != 0 && LSMRC_SH_XMODE != 0;
-    uint32_t x_phase = 0, h_phase = 0;
+    ShRow<PL> row;
+    row.tile = tile;
+    row.bar_x = &bar_x[team];
+    row.readers = &s_readers[team];
+    row.tmem = tmem;
+    row.x_phase = 0;
+    row.x_tma = p.x_tma != 0 && LSMRC_SH_XMODE != 0;
+    row.t = t, row.lane = lane, row.wt = wt, row.team = team, row.q = q, row.k1 = k1;
+    uint32_t h_phase = 0;
 
     for (;;) {
         if (threadIdx.x == 0) {
@@ -1437,65 +1552,23 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
 #pragma unroll
         for (int sl = 0; sl < 32; ++sl) acc[sl] = make_float2(0.f, 0.f);
 
-        if (x_tma && t == 0) {
-            fence_proxy_async();  // the tile doubled as the previous item's demap byte buffer
-            mbar_expect_tx(&bar_x[team], ROW_BYTES);
-            bulk_g2s(tile, x0, ROW_BYTES, &bar_x[team]);
-        }
+        if (row.x_tma && t == 0) sh_fetch_row<PL>(row, x0);  // (the tile doubled as the previous item's demap byte buffer)
         for (int a = 0; a < p.n_ant; ++a) {
             const float2* x_row = x0 + (long long)a * p.ant_stride;
             float2 v[32];
-            if (x_tma) {
-                mbar_wait(&bar_x[team], x_phase);
-                x_phase ^= 1u;
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) v[n1] = tile[n1 * T + t];  // as the copy laid the row out: linear
-                __syncwarp();  // stage 1 writes into columns of this warp's lanes only
-            } else {
-                row_load<PL>(v, x_row, t);
-                if (a + 1 < p.n_ant) prefetch_row<T, false>(x_row + p.ant_stride, N, t);
-            }
-            // ---- stage 1: 32-point transform over n1, twiddle W_N^(t*k1) by recurrence, into the swizzled tile
-            fft_reg<32>(v);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float2 w[8];
-                tmem_load8(tmem, 16 * c, w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = 8 * c + i;
-                    tile[PL::at(r, t)] = cmul(v[brev<32>(r)], w[i]);
-                }
-            }
-            team_sync<PL>(team);
-            // every warp of the team is past the previous antenna: its channel row may be replaced
+            sh_row_front<PL>(row, v, x_row, a + 1 < p.n_ant ? x_row + p.ant_stride : nullptr, [&]() {
+                // every warp of the team is past the previous antenna: its channel row may be replaced
 #if LSMRC_SH_HMODE
-            if (t == 0) {
-                mbar_expect_tx(&bar_h[team], ROW_BYTES);
-                bulk_g2s(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team]);
-            }
-#endif
-            // ---- stage 2 operands; the last warp to have read its own fetches the next antenna row into the tile
-            sh_stage2_read<PL>(v, tile, k1, q);
-            if (x_tma) {
-                __syncwarp();
-                if (lane == 0) {
-                    if (atomicAdd(&s_readers[team], 1u) == (unsigned)WPT - 1u) {
-                        s_readers[team] = 0u;
-                        if (a + 1 < p.n_ant) {
-                            fence_proxy_async();
-                            mbar_expect_tx(&bar_x[team], ROW_BYTES);
-                            bulk_g2s(tile, x_row + p.ant_stride, ROW_BYTES, &bar_x[team]);
-                        }
-                    }
+                if (t == 0) {
+                    mbar_expect_tx(&bar_h[team], ROW_BYTES);
+                    bulk_g2s(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team]);
                 }
-            } else {
-                team_sync<PL>(team);  // (plain-load fallback: the next row's stage 1 overwrites the tile)
-            }
-            fft_reg<32>(v);
+#endif
+            });
             // ---- twiddle W_T^(q*k2), radix-SH across the lanes, multiply-accumulate with conj(H)
             constexpr int JB = kShBatch;
 #if LSMRC_SH_HMODE
+            pin_values(v);  // the stage-2 transform stays ahead of the wait: it is the time the channel row has to land
             mbar_wait(&bar_h[team], h_phase);
             h_phase ^= 1u;
 #else
@@ -1532,6 +1605,167 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
         team_sync<PL>(team);  // every warp is done with the last row before the tile becomes the demap byte buffer
         mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(tile), valid, t, team);
         team_sync<PL>(team);  // the byte buffer aliases the tile the next item's first row is copied into
+    }
+    tmem_free_cols(s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+}
+
+// ---- pilot kernel of the shuffle-stage plans -----------------------------------------------------------------
+// Same job as MODE_PILOT above (virtual CTA = (frame, antenna group); teams take the group's antennas round-robin;
+// LS estimate, conj, sum_a |H|^2 with the fixed-order cross-team / cross-group sums) on the row pipeline of
+// lsmrc_data_sh, so that one pilot row costs what one data row costs -- the generic kernel needed 254 registers
+// (8 warps per SM) for the pilot values, reciprocals and energy partials and took twice as long per row.  Here the
+// per-bin constant of the LS divide, g = conj(X)/|X|^2 (cpuLS.hpp:240-241 with the reciprocal hoisted), sits in a
+// slot-major shared table where the data kernel keeps its channel row, and each thread reads its own 32 entries.
+// conj(H) goes to hwork slot-major and factored exactly as the data kernel's outputs are (Plan::unit_mul), so the
+// store is coalesced and needs no fix-up; the optional Hconj export in the reference layout is corrected.
+template <class PL, int MINB>
+__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_pilot_sh(const KernelParams p)
+{
+    constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, TEAMS = PL::TEAMS;
+    static_assert(SH > 1 && PL::ROW == T && PL::THREADS == 128, "shuffle-stage plans only");
+    extern __shared__ __align__(16) float2 smem[];
+    float2* s_g = smem;                 // [32][T] conj(X)/|X|^2 of (slot, thread); entry of bin 0 is zero
+    float2* s_tiles = s_g + N;          // [TEAMS][32][T]
+    __shared__ __align__(8) uint64_t bar_x[TEAMS];
+    __shared__ unsigned int s_readers[TEAMS];
+    __shared__ uint32_t s_tmem;
+    __shared__ unsigned int s_last;
+
+    const int team = threadIdx.x / T;
+    const int t = threadIdx.x % T;
+    const int lane = t & 31, wt = t >> 5;
+    const int q = lane % SH;
+    const int k1 = lane / SH + (32 / SH) * wt;
+    float2* tile = s_tiles + team * N;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TEAMS; ++i) {
+            mbar_init(&bar_x[i], 1);
+            s_readers[i] = 0u;
+        }
+        mbar_fence_init();
+    }
+    if (team == 0) {
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) {
+            const int bin = PL::bin_of(sl, t);
+            float2 g = make_float2(0.f, 0.f);
+            if (bin > 0) {
+                const float2 X = p.pilot_bin[bin - 1];
+                const float den = 1.0f / (X.x * X.x + X.y * X.y);
+                g = make_float2(X.x * den, -X.y * den);
+            }
+            s_g[sl * T + t] = g;
+        }
+    }
+    constexpr int kTmemCols = 128;
+    const uint32_t tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+    sh_fill_tmem<PL>(tmem, p.twiddles, t, q);
+    __syncthreads();
+
+    ShRow<PL> row;
+    row.tile = tile;
+    row.bar_x = &bar_x[team];
+    row.readers = &s_readers[team];
+    row.tmem = tmem;
+    row.x_phase = 0;
+    row.x_tma = p.x_tma != 0 && LSMRC_SH_XMODE != 0;
+    row.t = t, row.lane = lane, row.wt = wt, row.team = team, row.q = q, row.k1 = k1;
+
+    const int per_iter = p.n_groups * TEAMS;
+    const int n_iter = (p.n_ant + per_iter - 1) / per_iter;
+    const int n_virtual = p.n_frames * p.n_groups;
+    for (int vb = blockIdx.x; vb < n_virtual; vb += gridDim.x) {
+        const int f = vb / p.n_groups;
+        const int g = vb % p.n_groups;
+        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)p.first_sym * p.sym_stride + p.cp;
+        float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+        float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
+        float e[32];
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) e[sl] = 0.f;
+        // antenna of this team in iteration `it`; teams whose share has run out redo the last antenna and drop it
+        auto ant_of = [&](int it) { return (it * p.n_groups + g) * TEAMS + team; };
+        auto row_of = [&](int it) {
+            const int a = ant_of(it);
+            return x0 + (long long)(a < p.n_ant ? a : p.n_ant - 1) * p.ant_stride;
+        };
+        if (row.x_tma && t == 0) sh_fetch_row<PL>(row, row_of(0));
+        for (int it = 0; it < n_iter; ++it) {
+            const int a_raw = ant_of(it);
+            const bool a_ok = a_raw < p.n_ant;
+            const int a = a_ok ? a_raw : p.n_ant - 1;
+            float2 v[32];
+            sh_row_front<PL>(row, v, row_of(it), it + 1 < n_iter ? row_of(it + 1) : nullptr, []() {});
+            float2* hw_row = hw_frame + (long long)a * N + t;
+            float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
+            constexpr int JB = kShBatch;
+#pragma unroll
+            for (int c = 0; c < 16 / JB; ++c) {
+                float2 tw[2 * JB], gk[2 * JB];
+                tmem_load8(tmem, 64 + 16 * c, tw);
+#pragma unroll
+                for (int i = 0; i < 2 * JB; ++i) gk[i] = s_g[(2 * JB * c + i) * T + t];
+                float2 keep[JB], send[JB], A[JB], B[JB];
+#pragma unroll
+                for (int i = 0; i < JB; ++i) {
+                    keep[i] = cmul(v[2 * (JB * c + i)], tw[2 * i]);
+                    send[i] = cmul(v[2 * (JB * c + i) + 1], tw[2 * i + 1]);
+                }
+                sh_radix_batch<SH, JB>(keep, send, q, A, B);
+#pragma unroll
+                for (int i = 0; i < 2 * JB; ++i) {
+                    const int sl = 2 * JB * c + i;
+                    const float2 z = (i & 1) ? B[i / 2] : A[i / 2];
+                    // LS estimate H = Z / X (cpuLS.hpp:233-244) as Z * conj(X)/|X|^2, then conj (:303-307); z, and so
+                    // hc, carry the slot's unit factor, the energy does not care
+                    const float re = z.x * gk[i].x - z.y * gk[i].y;
+                    const float im = z.x * gk[i].y + z.y * gk[i].x;
+                    if (a_ok) {
+                        const float2 hc = make_float2(re, -im);
+                        hw_row[sl * T] = hc;
+                        if (hc_row) {
+                            const int bin = PL::bin_of(sl, t);
+                            if (bin > 0) hc_row[bin - 1] = PL::refix(sl, t, hc);
+                        }
+                        e[sl] += re * re + im * im;  // cpuLS.hpp:211-228 (the entry of bin 0 is zero)
+                    }
+                }
+            }
+        }
+        // deterministic cross-team sum of the energy partials, then cross-group by the last CTA of the frame
+        __syncthreads();
+        float* s_e = reinterpret_cast<float*>(s_tiles);  // [TEAMS][N] indexed by bin; aliases the tiles (no copy is in flight)
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) s_e[team * N + PL::bin_of(sl, t)] = e[sl];
+        __syncthreads();
+        for (int bin = 1 + (int)threadIdx.x; bin < N; bin += PL::THREADS) {
+            float acc = s_e[bin];
+#pragma unroll
+            for (int tm = 1; tm < TEAMS; ++tm) acc += s_e[tm * N + bin];
+            float* dst = (p.n_groups == 1) ? (p.hsqrd + (long long)f * K - 1) : (p.epart + ((long long)f * p.n_groups + g) * N);
+            dst[bin] = acc;
+        }
+        if (p.n_groups > 1) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int prev = atomicAdd(p.counters + f, 1u);
+                s_last = (prev == (unsigned)p.n_groups - 1u);
+                if (s_last) p.counters[f] = 0u;  // self-reset for the next launch
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const float* ep = p.epart + (long long)f * p.n_groups * N;
+                for (int bin = 1 + (int)threadIdx.x; bin < N; bin += PL::THREADS) {
+                    float acc = __ldcg(ep + bin);
+                    for (int gg = 1; gg < p.n_groups; ++gg) acc += __ldcg(ep + (long long)gg * N + bin);
+                    p.hsqrd[(long long)f * K + bin - 1] = acc;
+                }
+            }
+        }
+        __syncthreads();  // the partial-energy buffer aliases the tiles the next virtual CTA copies into
     }
     tmem_free_cols(s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
 }
