@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the c5 latency and other-config legs")
+    ap.add_argument("--no-scaling-c4", action="store_true", help="skip the config-4 block that every rank runs")
     return ap.parse_args()
 
 
@@ -141,6 +142,167 @@ def profile_traffic_per_frame(cfg_name):
         except Exception:
             pass
     return None
+
+
+def pin_to_gpu_numa(local):
+    """Run this rank on the cores of the NUMA node its GPU hangs off (first-touch then places the pinned staging
+    buffers there too).  Returns a short description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bdf = out.lower().replace("00000000:", "0000:")
+        base = "/sys/bus/pci/devices/" + bdf
+        node = open(base + "/numa_node").read().strip()
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (ids & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        return {"gpu_pci": bdf, "numa_node": int(node), "cpus": cpus, "pinned_to": len(use)}
+    except Exception as e:  # affinity is an optimisation, never a failure
+        return {"error": str(e)[:120]}
+
+
+def cpu_strong_baseline(cfg, budget_s=8.0):
+    """'Strong CPU' comparator promised in BASELINE.md: the same chain (CP strip, FFT, LS, MRC, hard demap left out)
+    as a vectorised torch pipeline on all host cores -- torch.fft on CPU is MKL/pocketfft, multi-threaded.  It is NOT
+    the reference's code (that is cpu_baseline / --impl reference); it answers 'what would a tuned CPU library do'."""
+    import numpy as np
+    import torch
+
+    import ofdm_b200 as m
+
+    A, N, C, S, K = cfg.n_ant, cfg.fft_size, cfg.cp_len, cfg.n_sym, cfg.K
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    F = max(1, min(8, int(1.5e9 // cfg.rx_bytes_per_frame)))
+    g = torch.Generator().manual_seed(5)
+    rx = torch.view_as_complex(torch.randn((F, S, A, N + C, 2), generator=g))
+    xb = torch.from_numpy(m.synth.asc_to_bin(m.synth.make_pilot(K, cfg.seed)))
+
+    def run():
+        y = torch.fft.fft(rx[..., C:], dim=-1)[..., 1:]           # [F,S,A,K], DC dropped
+        h = y[:, 0] / xb                                           # LS estimate [F,A,K]
+        e = (h.real ** 2 + h.imag ** 2).sum(1)                     # sum_a |H|^2 [F,K]
+        out = (y[:, 1:] * h.conj()[:, None]).sum(2) / e[:, None]   # MRC [F,S-1,K]
+        return torch.roll(out, (K + 1) // 2, dims=-1)              # ascending frequency
+
+    run()
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        run()
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 200:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": reps * F * cfg.antenna_samples_per_frame / dt, "unit": UNIT, "cores": cores, "kind": "torch-cpu",
+            "sample": f"{reps} passes over {F} frames of {cfg.name} ({dt:.1f} s): torch.fft.fft + vectorised LS/MRC on {cores} threads "
+                      f"(torch {torch.__version__}); not the reference's code, no demapper"}
+
+
+def h2d_ceiling(dev, nbytes, dist, world, reps=10):
+    """What the box's PCIe / host memory delivers to N GPUs at once: every rank copies `nbytes` from a pinned buffer
+    with plain cudaMemcpyAsync (three copies in flight), barrier both sides, max over ranks."""
+    import torch
+
+    n = max(1, nbytes // 3)
+    src = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    for b in src:
+        b.fill_(1)  # first touch on this rank's NUMA node
+    dst = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(3)]
+    streams = [torch.cuda.Stream(dev) for _ in range(3)]
+
+    def once():
+        for i in range(3):
+            with torch.cuda.stream(streams[i]):
+                dst[i].copy_(src[i], non_blocking=True)
+
+    once()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return world * 3 * n * reps / float(t.item()) / 1e9
+
+
+def scaling_c4_leg(m, dev, local, rank, world, dist, peak, frames=512, steps=5, warmup=2, unique=64):
+    """BASELINE config 4 -- the named scaling run: 4096-pt FFT, 256 antennas, 64-QAM, 512 frames per GPU (weak scaling,
+    64 GB of antenna samples resident per GPU), every rank on its own frames, no collective on the path.  Runs on ALL
+    ranks of every --gpus N line; time = max over ranks."""
+    import numpy as np
+    import torch
+
+    cfg = m.CONFIGS["c4"]
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    frames = int(min(frames, max(unique, (free_b * 0.8) // cfg.rx_bytes_per_frame)))
+    uniq = min(unique, frames)
+    rx_u, pilot_asc, src = m.synth.make_frames_torch(uniq, cfg, dev, seed=cfg.seed + 1000 * rank, chunk=4)
+    rx = torch.empty((frames, cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len), dtype=torch.complex64, device=dev)
+    for f0 in range(0, frames, uniq):   # distinct frames generated once, repeated to fill the batch
+        nf = min(uniq, frames - f0)
+        rx[f0:f0 + nf] = rx_u[:nf]
+    del rx_u
+    rx_f = torch.view_as_real(rx)
+    comb = torch.empty((frames, cfg.n_sym - 1, cfg.K, 2), device=dev, dtype=torch.float32)
+    bits = torch.empty((frames, cfg.n_sym - 1, cfg.bits_row_bytes), device=dev, dtype=torch.uint8)
+    stream = torch.cuda.current_stream(dev)
+    assert stream.cuda_stream != 0, "the bench runs on its own non-default stream"
+    with m.LsMrcReceiver.from_config(cfg, device=local) as r:
+        r.set_pilot(pilot_asc)
+        r.set_stream(stream.cuda_stream)
+        for _ in range(warmup):
+            r.demod_frames_device(rx_f, frames, comb, bits)
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        r.set_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            r.demod_frames_device(rx_f, frames, comb, bits)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        p_ms, d_ms = r.kernel_ms_history(steps)
+        plan = r.describe_plan()
+        r.set_stream(None)
+    # every decoded frame against the transmitted bits (the repeated frames against the source of their original)
+    want = torch.from_numpy(m.synth.pack_bits_rows(src.cpu().numpy(), cfg.qam_bits)).to(dev)
+    errs = 0
+    for f0 in range(0, frames, uniq):
+        nf = min(uniq, frames - f0)
+        x = bits[f0:f0 + nf] ^ want[:nf]
+        errs += int((x != 0).sum().item())      # bytes that differ
+    t = torch.tensor([ms, float(errs)], device=dev, dtype=torch.float64)
+    tmax = t.clone()
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms_max = float(tmax[0].item())
+    per_gpu_gbs = frames * steps * cfg.algorithmic_bytes_per_frame / (ms_max * 1e-3) / 1e9
+    del rx, rx_f, comb, bits, want
+    torch.cuda.empty_cache()
+    return {"workload": "c4: 4096-pt FFT, CP 288, 256 antennas, 1 pilot + 13 data symbols, 64-QAM", "scaling": "weak",
+            "frames_per_gpu": frames, "distinct_frames_per_gpu": uniq, "steps": steps, "warmup": warmup,
+            "input_bytes_per_gpu": frames * cfg.rx_bytes_per_frame, "ms_per_step": ms_max / steps,
+            "value": world * frames * steps * cfg.antenna_samples_per_frame / (ms_max * 1e-3), "unit": UNIT,
+            "algorithmic_gbs_per_gpu": per_gpu_gbs, "frac_of_hbm_peak": per_gpu_gbs / peak,
+            "pilot_kernel_ms": statistics.mean(p_ms), "data_kernel_ms": statistics.mean(d_ms),
+            "differing_bit_bytes_vs_source_all_ranks": int(t[1].item()) if dist is not None else errs,
+            "frames_checked_per_gpu": frames, "plan": plan}
 
 
 def cpu_baseline(cfg, n_threads, budget_s=12.0):
@@ -312,6 +474,7 @@ def frontend_leg(m, dev_index, peak):
     rx = torch.empty((cfg.n_sym, cfg.n_ant, cfg.fft_size + cfg.cp_len, 2), device=dev)
     with m.LsMrcReceiver.from_config(cfg, device=dev_index) as r:
         stream = torch.cuda.current_stream(dev)
+        assert stream.cuda_stream != 0, "the bench runs on its own non-default stream"
         r.set_stream(stream.cuda_stream)
         for _ in range(3):
             off = r.sync_correlate(b1, cfg.n_ant, samps, pn, L, 0.5)[0]
@@ -410,12 +573,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the receiver has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
+
+    # a stream of our own, made torch's current one before anything is enqueued (torch's default stream has handle 0,
+    # which lsmrc_set_stream reads as "back to the handle's own stream"): the synthetic-data generator, the torch
+    # events and the library's launches all share it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     F = args.frames or DEFAULT_FRAMES[cfg.name]
     Fe = args.e2e_frames or DEFAULT_E2E_FRAMES[cfg.name]
@@ -428,7 +598,6 @@ def main():
     chunk_frames = max(1, min(Fe, int(round(450e6 / cfg.rx_bytes_per_frame)) or 1))
     rcv = m.LsMrcReceiver.from_config(cfg, max_frames=chunk_frames, device=local, n_lanes=3)
     rcv.set_pilot(pilot_asc)
-    stream = torch.cuda.current_stream(dev)
     rcv.set_stream(stream.cuda_stream)
 
     def step():
@@ -480,7 +649,8 @@ def main():
     peak, peak_src = measured_peak_gbs()
     achieved = F * data_bytes_per_frame / (data_ms * 1e-3) / 1e9
     tpf = profile_traffic_per_frame(cfg.name)
-    roofline = {"bound": "hbm", "kernel": "lsmrc_kernel<MODE_DATA> (FFT + MRC + demap)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": ("lsmrc_data_sh" if cfg.fft_size >= 2048 else "lsmrc_kernel<MODE_DATA>") + " (FFT + MRC + demap)",
+                "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (tpf * F) if tpf else None, "algorithmic_bytes_per_launch": F * data_bytes_per_frame,
                 "kernel_ms": data_ms, "pilot_kernel_ms": pilot_ms, "kernel_share_of_step": data_ms / (data_ms + pilot_ms),
@@ -509,7 +679,10 @@ def main():
         # the host path leaves the cyclic prefix behind (strided H2D copy): count the bytes actually moved
         strip = "h2d=strip-cp" in rcv.describe_plan()
         h2d = int(h_rx.nbytes * cfg.fft_size // (cfg.fft_size + cfg.cp_len)) if strip else int(h_rx.nbytes)
+        ceiling = h2d_ceiling(dev, h2d, dist, world)
         e2e = {"value": world * Fe * n_e2e * cfg.antenna_samples_per_frame / dt, "unit": UNIT,
+               "h2d_ceiling_gbs": ceiling, "h2d_frac_of_ceiling": (world * h2d * n_e2e / dt / 1e9) / ceiling,
+               "h2d_ceiling_what": f"{world} rank(s) copying the same bytes from plain pinned buffers with cudaMemcpyAsync at the same time",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_comb.nbytes + h_bits.nbytes),
                "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e, "api": "lsmrc_demod_frames_host (pinned host buffers, 3 lanes)",
                "h2d_gbs": world * h2d * n_e2e / dt / 1e9, "host_input_bytes_per_step": int(h_rx.nbytes),
@@ -519,6 +692,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(cfg, os.cpu_count() or 1)
+        cpu["strong"] = cpu_strong_baseline(cfg)
+        if e2e is not None:   # the host-buffer figure next to each CPU figure (the 1-core reference build is the weakest)
+            e2e["over_cpu_port_all_cores"] = e2e["value"] / cpu["value"]
+            e2e["over_cpu_strong_torch"] = e2e["value"] / cpu["strong"]["value"]
+            if cpu.get("reference_1core"):
+                e2e["over_reference_1core"] = e2e["value"] / cpu["reference_1core"]["value"]
 
     # ---- long-run behaviour: this kernel is fp32-heavy (about 40 TFLOP/s at full clocks) and reaches the
     # 1000 W board power cap after ~0.15 s of back-to-back steps, after which the SM clock drops; the
@@ -540,10 +719,16 @@ def main():
         sustained = {"steps": n_long, "measured_over_last": len(dl), "data_kernel_ms": dms, "achieved": ach, "frac": ach / peak,
                      "value": F * cfg.antenna_samples_per_frame / ((dms + statistics.mean(pl)) * 1e-3), "clocks": ck2}
 
+    # ---- BASELINE config 4 on every rank (the named scaling configuration); c2 stays `value`
+    del rx, rx_f, comb, bits
+    torch.cuda.empty_cache()
+    scaling_c4 = None
+    if not args.no_scaling_c4:
+        rcv.set_stream(None)
+        scaling_c4 = scaling_c4_leg(m, dev, local, rank, world, dist, peak)
+
     latency = others = frontend = ring_stream = None
     if rank == 0 and world == 1 and not args.no_extras:
-        del rx, rx_f, comb, bits
-        torch.cuda.empty_cache()
         latency = latency_leg(m, local)
         others = other_configs_leg(m, local, peak)
         frontend = frontend_leg(m, local, peak)
@@ -559,7 +744,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, F, Fe), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks, "plan": rcv.describe_plan(), "latency": latency,
-                "sustained": sustained, "other_configs": others, "frontend": frontend, "ring_stream": ring_stream,
+                "sustained": sustained, "scaling_c4": scaling_c4, "other_configs": others, "frontend": frontend,
+                "ring_stream": ring_stream, "affinity": affinity,
                 "parity": {"bit_errors_vs_source": bit_errors, "ber": ber, "frames_checked": 2}}
         print(json.dumps(line), flush=True)
     rcv.close()

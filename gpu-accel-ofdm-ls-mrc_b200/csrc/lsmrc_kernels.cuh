@@ -327,6 +327,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// L2 eviction priorities for bulk copies.  Antenna samples are read exactly once: evict_first keeps them from pushing
+// out the channel rows (hwork), which every data symbol of a frame re-reads and which should be served from L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 // orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) ones
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -1388,7 +1410,7 @@ __device__ __forceinline__ void sh_fetch_row(const ShRow<PL>& r, const float2* x
 {
     fence_proxy_async();  // the tile's earlier generic-proxy accesses are ordered before the copy
     mbar_expect_tx(r.bar_x, (uint32_t)(PL::N * sizeof(float2)));
-    bulk_g2s(r.tile, x_row, (uint32_t)(PL::N * sizeof(float2)), r.bar_x);
+    bulk_g2s_hint(r.tile, x_row, (uint32_t)(PL::N * sizeof(float2)), r.bar_x, l2_policy_evict_first());
 }
 
 // Everything of a row up to the stage-2 transform: samples out of the tile (or by plain loads when rows are not
@@ -1561,7 +1583,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
 #if LSMRC_SH_HMODE
                 if (t == 0) {
                     mbar_expect_tx(&bar_h[team], ROW_BYTES);
-                    bulk_g2s(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team]);
+                    bulk_g2s_hint(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team], l2_policy_evict_last());
                 }
 #endif
             });

@@ -54,8 +54,13 @@ struct dim3 {
 #ifndef LSMRC_QAM_BITS
 #define LSMRC_QAM_BITS 2  // demapper order; the reference has no demapper
 #endif
-#ifndef mode
-#define mode 0  // 0 = slave: attach to a ring somebody else created (gpuLS.cuh:57)
+// 0 = slave: attach to a ring somebody else created.  The reference makes this a macro called `mode`
+// (gpuLS.cuh:57); a macro of that name breaks every later header with a parameter called mode (cublas_v2.h,
+// which gpuLS_main.cu:37 includes next), so it is honoured when the build defines it but never defined here.
+#ifdef mode
+constexpr int kLsmrcRingMode = (mode);
+#else
+constexpr int kLsmrcRingMode = 0;
 #endif
 
 class gpuLS {
@@ -64,7 +69,7 @@ class gpuLS {
     lsmrc_handle handle = nullptr;
 
     // Reference constructor (gpuLS.cu:43-47): opens the ring named shmemID as slave, macro dims.
-    gpuLS() : gpuLS(numOfRows, dimension, prefix, lenOfBuffer, LSMRC_QAM_BITS, lenOfBuffer, std::string(shmemID), mode, 0) {}
+    gpuLS() : gpuLS(numOfRows, dimension, prefix, lenOfBuffer, LSMRC_QAM_BITS, lenOfBuffer, std::string(shmemID), kLsmrcRingMode, 0) {}
 
     // Runtime dimensions.  ring_slots == 0 -> no ring (device / host tensors only).
     gpuLS(int rows, int cols, int cp, int n_sym, int qam_bits, int ring_slots, const std::string& shm_uid,

@@ -68,3 +68,28 @@ def test_configs_match_baseline_table(ofdm):
     # SURVEY 8d byte formula (+4K for the sum|H|^2 row and per-row padded bit packing)
     assert abs(c["c2"].algorithmic_bytes_per_frame - 54346414) < 5000
     assert abs(c["c4"].algorithmic_bytes_per_frame - 126292879) < 20000
+
+
+def test_reference_gpu_driver_compiles_unmodified_against_the_drop_in_headers():
+    """gpuLS_main.cu of the reference builds, byte for byte, against host/gpuLS.cuh and host/ShMemSymBuff_cucomplex.hpp
+    and links with the C-ABI library (recipe: oracle/Makefile, _ref/gpuLS_main_ref_%).  The -m gpu suite runs it."""
+    import shutil
+    import subprocess
+
+    if not os.path.isdir("/root/reference") or shutil.which("nvcc") is None:
+        pytest.skip("needs /root/reference and nvcc (build container)")
+    import ofdm_b200
+
+    ofdm_b200.load_library()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "gpuLS_main_ref_A4_N64_C16_S16")
+    if os.path.exists(exe):
+        os.unlink(exe)
+    r = subprocess.run(["make", "-C", os.path.join(root, "oracle"), "--no-print-directory", "_ref/gpuLS_main_ref_A4_N64_C16_S16"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and os.path.exists(exe), r.stdout + r.stderr
+    src = os.path.realpath(os.path.join(root, "oracle", "_ref", "src", "gpuLS_main.cu"))
+    assert src == "/root/reference/gpuLS_main.cu"     # a link to the reference's file, not a copy
+    nm = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for sym in ("lsmrc_first_vector", "lsmrc_demod_one_symbol", "lsmrc_set_pilot_file"):
+        assert sym in nm, f"the reference driver does not reach the C ABI through {sym}"

@@ -208,3 +208,42 @@ def test_latency_harness_reports_every_path(host_bins):
     assert d["device_one_launch"]["kernels_per_frame"] == 1 and d["device_two_kernels"]["kernels_per_frame"] == 2
     assert d["device_one_launch"]["p50_us"] < d["device_two_kernels"]["p50_us"]
     assert d["host_one_launch_in_place"]["p50_us"] < d["host_two_kernels"]["p50_us"]
+
+
+# ---- the reference's OWN GPU driver, compiled unmodified against the drop-in headers -----------------------------
+@pytest.mark.parametrize("dims", [(4, 64, 16, 16, 2), (8, 1024, 64, 6, 4)], ids=lambda d: "A%d_N%d_C%d_S%d" % d[:4])
+def test_reference_gpu_driver_unmodified_runs_on_the_facade(ofdm, oracle, host_bins, tmp_path, dims):
+    """oracle/_ref/gpuLS_main_ref_* is /root/reference/gpuLS_main.cu, byte for byte, built by oracle/Makefile against
+    host/gpuLS.cuh + host/ShMemSymBuff_cucomplex.hpp and linked with the C-ABI library.  Fed through the ring by
+    ring_feeder it must write the oracle's combined symbols to Output_gpu.dat (gpuLS_main.cu:104-126) and the five
+    timers to time_gpu.dat (printTimes / storeTimes, :139-140)."""
+    A, N, C, S, b = dims
+    exe = os.path.join(ROOT, "oracle", "_ref", "gpuLS_main_ref_A%d_N%d_C%d_S%d" % (A, N, C, S))
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gpuLS_main_ref_* not built (needs /root/reference and nvcc at build time)")
+    K = N - 1
+    d = ofdm.synth.make_frames(1, A, N, C, S, b, snr_db=15.0, seed=77)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    shm = "/blah"                                     # hard-coded in the reference (shmemID)
+    if os.path.exists("/dev/shm" + shm):
+        os.unlink("/dev/shm" + shm)
+    d["rx"].tofile(tmp_path / "rx.bin")
+    d["pilot_asc"].tofile(tmp_path / "Pilots.dat")    # fileNameForX
+    dimargs = ["--rows", str(A), "--cols", str(N), "--prefix", str(C), "--syms", str(S), "--ring", str(S), "--shm", shm]
+    feeder = subprocess.Popen([os.path.join(host_bins, "ring_feeder"), "--file", str(tmp_path / "rx.bin"), "--frames", "1"] + dimargs)
+    try:
+        r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        feeder.wait(timeout=60)
+    finally:
+        if feeder.poll() is None:
+            feeder.kill()
+        if os.path.exists("/dev/shm" + shm):
+            os.unlink("/dev/shm" + shm)
+    comb = np.fromfile(tmp_path / "Output_gpu.dat", np.complex64).reshape(1, S - 1, K)
+    assert_close(comb, ref["combined"], "reference gpuLS_main.cu on the facade: combined")
+    bits = np.stack([oracle.demap_row(comb[0, s], b)[0] for s in range(S - 1)])[None]
+    assert np.array_equal(bits, ref["bits"])
+    times = np.fromfile(tmp_path / "time_gpu.dat", np.float32)
+    assert times.shape == (5,) and np.isfinite(times).all() and (times >= 0).all(), times
+    assert "ChanEst" in r.stdout                      # printTimes(true) table, ShMemSymBuff_gpu.hpp:153-162

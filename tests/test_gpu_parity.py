@@ -304,3 +304,41 @@ def test_full_baseline_dimensions_match_oracle_and_reference_outputs(ofdm, oracl
     assert_bits_match(got["bits"], g["bits"], g["combined"], b, name + " vs reference build", got_combined=got["combined"])
     # and the frame decodes to what was transmitted (20 dB / 15 dB with 64+ antennas: error free)
     assert np.array_equal(got["bits"], ofdm.synth.pack_bits_rows(g["src_idx"], b))
+
+
+@pytest.mark.gpu
+def test_caller_stream_orders_the_launches_and_null_returns_to_the_own_stream(ofdm, oracle):
+    """lsmrc_set_stream: device-resident calls run on the caller's stream (work enqueued on it before and after is
+    ordered with the kernels); NULL switches back to the handle's own stream (include/ofdm_lsmrc.h)."""
+    import torch
+
+    A, N, C, S, b, F = 6, 1024, 64, 5, 4, 24
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=15.0, seed=31)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    dev = torch.device("cuda:0")
+    user = torch.cuda.Stream(dev)
+    host_rx = torch.view_as_real(torch.from_numpy(d["rx"])).contiguous().pin_memory()
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(d["pilot_asc"])
+        r.set_oneshot(0)
+        for use_user in (True, False):
+            rx = torch.empty_like(host_rx, device=dev)
+            comb = torch.zeros((F, S - 1, K, 2), device=dev)
+            bits = torch.zeros((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+            if use_user:
+                r.set_stream(user.cuda_stream)
+                with torch.cuda.stream(user):
+                    rx.copy_(host_rx, non_blocking=True)        # the kernels must wait for this copy ...
+                    r.demod_frames_device(rx, F, comb, bits)
+                    out = comb.to("cpu", non_blocking=True)     # ... and this copy for the kernels
+                user.synchronize()
+            else:
+                r.set_stream(None)                              # back to the handle's own stream
+                rx.copy_(host_rx)
+                torch.cuda.synchronize(dev)
+                r.demod_frames_device(rx, F, comb, bits)
+                r.sync()
+                out = comb.cpu()
+            assert_close(torch.view_as_complex(out).numpy(), ref["combined"], f"combined (user stream: {use_user})")
+            assert np.array_equal(bits.cpu().numpy(), ref["bits"])
