@@ -508,7 +508,7 @@ def ring_stream_leg(m, n_frames=192, feeder_threads=None, config="c3", lanes=3, 
 
     cfg = m.CONFIGS[config]
     if feeder_threads is None:
-        feeder_threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+        feeder_threads = max(1, min(12, (os.cpu_count() or 2) - 4))
     host = os.path.join(ROOT, "gpu-accel-ofdm-ls-mrc_b200", "host")
     if subprocess.run(["make", "-C", host, "--no-print-directory"], capture_output=True).returncode != 0:
         return {"error": "host programs did not build"}
@@ -527,7 +527,8 @@ def ring_stream_leg(m, n_frames=192, feeder_threads=None, config="c3", lanes=3, 
                                    "--repeat", str(n_frames // base), "--threads", str(feeder_threads)] + dims)
         try:
             r = subprocess.run([os.path.join(host, "bin", "stream_main"), "--qam", str(cfg.qam_bits), "--frames", str(n_frames),
-                                "--pilots", os.path.join(d, "Pilots.dat"), "--no-output", "--lanes", str(lanes), "--batch", str(batch)] + dims,
+                                "--pilots", os.path.join(d, "Pilots.dat"), "--no-output", "--lanes", str(lanes), "--batch", str(batch),
+                                "--trace", os.path.join(d, "trace.csv")] + dims,
                                cwd=d, capture_output=True, text=True, timeout=300)
             feeder.wait(timeout=60)
         finally:
@@ -538,6 +539,9 @@ def ring_stream_leg(m, n_frames=192, feeder_threads=None, config="c3", lanes=3, 
         if r.returncode != 0:
             return {"error": (r.stdout + r.stderr)[-300:]}
         out = json.loads(r.stdout.strip().splitlines()[-1])
+        ts = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "trace_summary.py"), os.path.join(d, "trace.csv")],
+                            capture_output=True, text=True)
+        out["overlap"] = ts.stdout.strip().splitlines() if ts.returncode == 0 else None
         out["workload"] = (f"{config}: {cfg.fft_size}-pt FFT, {cfg.n_ant} antennas, {cfg.n_sym}-symbol slots, ring of {ring} slots "
                            f"({cfg.rx_bytes_per_frame / 1e6:.1f} MB per frame), one producer process filling slots with {feeder_threads} threads")
         out["note"] = note or ("bounded by the producer's memcpy into the ring, then by PCIe; the consumer overlaps H2D, both "

@@ -60,6 +60,9 @@ ABI = {
     "lsmrc_host_register": (c_int, [c_void_p, c_void_p, c_size_t]),
     "lsmrc_host_unregister": (c_int, [c_void_p, c_void_p]),
     "lsmrc_set_stream": (c_int, [c_void_p, c_void_p]),
+    "lsmrc_ring_trace": (c_int, [c_void_p, c_int, c_void_p]),
+    "lsmrc_device_count": (c_int, []),
+    "lsmrc_device_pci_bus_id": (c_int, [c_int, c_char_p, c_size_t]),
     "lsmrc_sync": (c_int, [c_void_p]),
     "lsmrc_estimate_noise_var": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lsmrc_llr_from_combined": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

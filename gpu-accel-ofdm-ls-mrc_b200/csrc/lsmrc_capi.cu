@@ -446,6 +446,7 @@ struct Lane {
     ChanState ch;
     cudaStream_t st = nullptr;
     cudaEvent_t copied = nullptr, done = nullptr;
+    cudaEvent_t t_start = nullptr, t_kernels = nullptr;  // timeline of the ring path (lsmrc_ring_trace): submission enqueued, kernels finished
     float2* d_rx = nullptr;     // [max_frames][S][A][N+C]
     float2* d_hconj = nullptr;  // [max_frames][A][K] (reference layout, only when the caller wants it back)
     float2* d_comb = nullptr;   // [max_frames][S-1][K]
@@ -509,6 +510,7 @@ struct lsmrc_ctx {
     uint8_t* h_one_bits = nullptr;
     bool have_channel = false;
     std::vector<Lane> lanes;
+    cudaEvent_t ring_epoch = nullptr;     // time zero of lsmrc_ring_trace: the first ring submission of the handle
     unsigned long long* d_hit = nullptr;  // frame-sync first-hit key
     float* d_noise_part = nullptr;        // [frames][S-1] row partials of the noise estimator
     size_t noise_part_rows = 0;
@@ -800,8 +802,10 @@ int alloc_lane(lsmrc_ctx* h, Lane& L)
     const size_t F = (size_t)c.max_frames;
     const size_t nd = (size_t)(c.n_sym > 1 ? c.n_sym - 1 : 1);
     CK(h, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
-    CK(h, cudaEventCreateWithFlags(&L.copied, cudaEventDisableTiming));
-    CK(h, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    CK(h, cudaEventCreate(&L.copied));  // (timing enabled: the four events of a lane are the timeline of lsmrc_ring_trace)
+    CK(h, cudaEventCreate(&L.done));
+    CK(h, cudaEventCreate(&L.t_start));
+    CK(h, cudaEventCreate(&L.t_kernels));
     CK(h, cudaMalloc(&L.d_rx, F * h->frame_elems * sizeof(float2)));
     CK(h, cudaMalloc(&L.d_hconj, F * (size_t)c.n_ant * h->K * sizeof(float2)));
     {
@@ -829,6 +833,8 @@ void free_lane(Lane& L)
     cudaFreeHost(L.h_hconj);
     if (L.copied) cudaEventDestroy(L.copied);
     if (L.done) cudaEventDestroy(L.done);
+    if (L.t_start) cudaEventDestroy(L.t_start);
+    if (L.t_kernels) cudaEventDestroy(L.t_kernels);
     if (L.st) cudaStreamDestroy(L.st);
     L = Lane();
 }
@@ -929,6 +935,26 @@ size_t lsmrc_rx_frame_elems(const lsmrc_config* c)
 }
 
 int lsmrc_supported_fft_size(int fft_size) { return find_plan(fft_size) != nullptr; }
+
+int lsmrc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lsmrc_device_pci_bus_id(int device, char* buf, size_t buf_len)
+{
+    if (!buf || buf_len < 13) return LSMRC_ERR_INVALID;
+    if (cudaDeviceGetPCIBusId(buf, (int)buf_len, device) != cudaSuccess) {
+        cudaGetLastError();
+        return LSMRC_ERR_CUDA;
+    }
+    return LSMRC_OK;
+}
 
 int lsmrc_create(const lsmrc_config* cfg, lsmrc_handle* out)
 {
@@ -1045,6 +1071,7 @@ int lsmrc_destroy(lsmrc_handle h)
     for (int i = 0; i < lsmrc_ctx::kEvRing; ++i)
         for (int j = 0; j < 3; ++j)
             if (h->ev[i][j]) cudaEventDestroy(h->ev[i][j]);
+    if (h->ring_epoch) cudaEventDestroy(h->ring_epoch);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
     delete h;
@@ -1378,6 +1405,17 @@ int lsmrc_get_channel_device(lsmrc_handle h, void* d_hconj, void* d_hsqrd)
 
 // ---- ring lanes -----------------------------------------------------------------------
 
+// first event of a submission's timeline; the very first submission of the handle also defines time zero
+static cudaError_t ring_mark_start(lsmrc_ctx* h, Lane& L)
+{
+    if (!h->ring_epoch) {
+        cudaError_t e = cudaEventCreate(&h->ring_epoch);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaEventRecord(h->ring_epoch, L.st)) != cudaSuccess) return e;
+    }
+    return cudaEventRecord(L.t_start, L.st);
+}
+
 static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L, int n_frames)
 {
     const lsmrc_config& c = h->cfg;
@@ -1385,6 +1423,7 @@ static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L, int n_frames)
     CK(h, cudaEventRecord(L.copied, L.st));
     int rc = launch_frames(h, L.st, L.d_rx, n_frames, L.ch, L.d_hconj, nullptr, L.d_comb, L.d_bits, false);
     if (rc != LSMRC_OK) return rc;
+    CK(h, cudaEventRecord(L.t_kernels, L.st));
     if (nd > 0) {
         CK(h, cudaMemcpyAsync(L.h_comb, L.d_comb, n_frames * nd * h->K * sizeof(float2), cudaMemcpyDeviceToHost, L.st));
         CK(h, cudaMemcpyAsync(L.h_bits, L.d_bits, n_frames * nd * h->row_bytes, cudaMemcpyDeviceToHost, L.st));
@@ -1426,6 +1465,7 @@ static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_f
     const int rc = launch_frames(h, L.st, static_cast<const float2*>(a1), n_frames, L.ch, L.a_hconj, nullptr, L.a_comb, L.a_bits, false, &lay);
     if (rc != LSMRC_OK) return rc;
     CK(h, cudaEventRecord(L.copied, L.st));  // the slots are free once the kernel has read them
+    CK(h, cudaEventRecord(L.t_kernels, L.st));
     CK(h, cudaEventRecord(L.done, L.st));
     L.busy = true;
     L.ring_frames = n_frames;
@@ -1444,6 +1484,7 @@ int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_
     Lane& L = h->lanes[(size_t)lane];
     const size_t slot_bytes = h->slot_elems * sizeof(float2);
     if (slot_stride_bytes < slot_bytes) return fail(h, LSMRC_ERR_INVALID, "slot stride smaller than a slot");
+    CK(h, ring_mark_start(h, L));
     if ((rc = ring_try_in_place(h, L, h_slots, h->cfg.n_sym, nullptr, slot_stride_bytes)) != 0) return rc < 0 ? rc : LSMRC_OK;
     if (slot_stride_bytes == slot_bytes) {
         CK(h, cudaMemcpyAsync(L.d_rx, h_slots, slot_bytes * h->cfg.n_sym, cudaMemcpyHostToDevice, L.st));
@@ -1467,6 +1508,7 @@ int lsmrc_ring_submit_frames(lsmrc_handle h, int lane, const void* h_first, int 
     if (rc != LSMRC_OK) return rc;
     Lane& L = h->lanes[(size_t)lane];
     const size_t slot_bytes = h->slot_elems * sizeof(float2);
+    CK(h, ring_mark_start(h, L));
     if (n_first > 0 && (rc = ring_try_in_place(h, L, h_first, n_first, h_second, slot_bytes, n_frames)) != 0) return rc < 0 ? rc : LSMRC_OK;
     if (n_first > 0) CK(h, cudaMemcpyAsync(L.d_rx, h_first, slot_bytes * n_first, cudaMemcpyHostToDevice, L.st));
     if (n_first < n_slots)
@@ -1509,6 +1551,16 @@ int lsmrc_ring_wait(lsmrc_handle h, int lane, const void** combined, const void*
     if (combined) *combined = L.h_comb;
     if (bits) *bits = L.h_bits;
     if (hconj) *hconj = L.h_hconj;
+    return LSMRC_OK;
+}
+
+int lsmrc_ring_trace(lsmrc_handle h, int lane, float* ms4)
+{
+    if (!h || !ms4 || lane < 0 || lane >= (int)h->lanes.size()) return fail(h, LSMRC_ERR_INVALID, "bad argument");
+    Lane& L = h->lanes[(size_t)lane];
+    if (!h->ring_epoch || L.busy) return fail(h, LSMRC_ERR_STATE, "collect the lane with lsmrc_ring_wait first");
+    cudaEvent_t ev[4] = {L.t_start, L.copied, L.t_kernels, L.done};
+    for (int i = 0; i < 4; ++i) CK(h, cudaEventElapsedTime(&ms4[i], h->ring_epoch, ev[i]));
     return LSMRC_OK;
 }
 

@@ -5,7 +5,8 @@
 // Creates the segment (master), waits for a consumer, streams the frames of a file.
 //
 //   ring_feeder --file rx.bin --rows A --cols N --prefix C --syms S --ring L [--frames F]
-//               [--shm /blah] [--repeat R] [--nowait] [--threads T]
+//               [--shm /blah] [--repeat R] [--nowait] [--threads T] [--stream-stores]
+// Slots are filled with non-temporal stores when --threads T > 1 or --stream-stores is given (see stream_copy).
 // --threads T > 1 copies every symbol into its slot with T helper threads (a radio front end delivers
 // the antennas in parallel; one memcpy thread tops out near 9 GB/s and would hide what the consumer can do).
 // rx.bin holds [F][S][A][N+C] complex64.  --nowait uses writeNextSymbolNoWait like the
@@ -20,6 +21,36 @@
 #include <vector>
 
 #include "ShMemSymBuff.hpp"
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+// Copy into a ring slot with non-temporal stores.  The slot is written once and next read by the GPU's DMA engine,
+// never by this CPU: ordinary stores would first read every destination line into the cache (a third of the memory
+// traffic of the copy) and then evict what the producer actually reuses.  Slots sit behind the ring's 12-byte header,
+// i.e. only 4-byte aligned, so the head and tail of the range are copied normally.
+static void stream_copy(void* dst, const void* src, size_t bytes)
+{
+#if defined(__SSE2__)
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    if (bytes < 256 || head > bytes) {
+        std::memcpy(d, s, bytes);
+        return;
+    }
+    std::memcpy(d, s, head);
+    d += head, s += head, bytes -= head;
+    const size_t n16 = bytes / 16;
+    for (size_t i = 0; i < n16; ++i)
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d) + i, _mm_loadu_si128(reinterpret_cast<const __m128i*>(s) + i));
+    std::memcpy(d + n16 * 16, s + n16 * 16, bytes - n16 * 16);
+    _mm_sfence();  // the stores are globally visible before the slot is committed to the consumer
+#else
+    std::memcpy(dst, src, bytes);
+#endif
+}
 
 // Splits one symbol copy over a few persistent helper threads (spin-synchronised: copies are ~100 us apart).
 class ParallelCopy {
@@ -37,7 +68,7 @@ class ParallelCopy {
     void copy(void* dst, const void* src, size_t bytes)
     {
         if (n_ == 1) {
-            std::memcpy(dst, src, bytes);
+            stream_copy(dst, src, bytes);
             return;
         }
         dst_ = static_cast<char*>(dst);
@@ -54,7 +85,7 @@ class ParallelCopy {
     {
         const size_t chunk = ((bytes_ + n_ - 1) / n_ + 63) & ~(size_t)63;
         const size_t b = chunk * (size_t)i, e = b + chunk < bytes_ ? b + chunk : bytes_;
-        if (b < e) std::memcpy(dst_ + b, src_ + b, e - b);
+        if (b < e) stream_copy(dst_ + b, src_ + b, e - b);
     }
     void loop(int i)
     {
@@ -81,7 +112,7 @@ class ParallelCopy {
 int main(int argc, char** argv)
 {
     int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, ring = 0, frames = -1, repeat = 1, threads = 1;
-    bool nowait = false;
+    bool nowait = false, stream_stores = false;
     std::string shm = shmemID, file;
     for (int i = 1; i < argc; ++i) {
         auto val = [&](const char* name) -> const char* {
@@ -100,6 +131,7 @@ int main(int argc, char** argv)
         else if ((v = val("--shm"))) shm = v;
         else if ((v = val("--file"))) file = v;
         else if (std::strcmp(argv[i], "--nowait") == 0) nowait = true;
+        else if (std::strcmp(argv[i], "--stream-stores") == 0) stream_stores = true;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
@@ -126,7 +158,7 @@ int main(int argc, char** argv)
         for (int f = 0; f < frames; ++f)
             for (int s = 0; s < syms; ++s) {
                 complexF* sym = buf.data() + ((size_t)f * syms + (size_t)s) * slot;
-                if (threads > 1) {
+                if (threads > 1 || stream_stores) {
                     // same protocol as writeNextSymbolWithWait, with the slot filled by the helper threads
                     complexF* dst = ringbuf.acquireWriteSlot();
                     if (!dst) break;  // reader gone

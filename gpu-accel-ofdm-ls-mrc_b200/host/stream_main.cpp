@@ -5,7 +5,10 @@
 // with a device-wide sync after every step (ShMemSymBuff_gpu.hpp:386-387, gpuLS.cu:365-401).
 //
 //   stream_main --rows A --cols N --prefix C --syms S --qam b --ring L --frames F [--shm /blah]
-//               [--lanes n] [--batch k] [--bits-ring /name [--bits-slots n]]
+//               [--lanes n] [--batch k] [--bits-ring /name [--bits-slots n]] [--gpus G] [--trace file]
+// --gpus G: one ring (<shm>_g), one worker thread and one receiver per GPU inside this process (the
+// reference is pinned to device 0, gpuLS_main.cu:69); --frames counts per GPU.
+// --trace file: per submission the CUDA-event times of its H2D, kernels and D2H (lsmrc_ring_trace), as CSV.
 // --lanes: submissions in flight on the GPU at once (default 3, or 4 for frames below 1 MB).
 // --batch: frames per submission when that many are already waiting in the ring (default 1, or 16 for frames below
 // 1 MB).  A ring shorter than lanes*batch frames + 1 slot (the default is (lanes*batch + 1)*S + 1) simply limits how
@@ -19,66 +22,76 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gpuLS.hpp"  // defines cudaEn before the ring header is seen
 #include "ShMemBitsBuff.hpp"
 
-int main(int argc, char** argv)
-{
+struct Args {
     int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, qam = LSMRC_QAM_BITS, ring = 0, frames = 1;
-    std::string shm = shmemID, pilots = fileNameForX, bits_ring;
-    int bits_slots = 8, n_lanes = 0, batch = 0;
+    std::string shm = shmemID, pilots = fileNameForX, bits_ring, trace;
+    int bits_slots = 8, n_lanes = 0, batch = 0, gpus = 1;
     bool write_out = true;
-    for (int i = 1; i < argc; ++i) {
-        auto val = [&](const char* name) -> const char* {
-            if (std::strcmp(argv[i], name) == 0 && i + 1 < argc) return argv[++i];
-            return nullptr;
-        };
-        const char* v;
-        if ((v = val("--rows"))) rows = atoi(v);
-        else if ((v = val("--cols"))) cols = atoi(v);
-        else if ((v = val("--prefix"))) cp = atoi(v);
-        else if ((v = val("--syms"))) syms = atoi(v);
-        else if ((v = val("--qam"))) qam = atoi(v);
-        else if ((v = val("--ring"))) ring = atoi(v);
-        else if ((v = val("--frames"))) frames = atoi(v);
-        else if ((v = val("--shm"))) shm = v;
-        else if ((v = val("--pilots"))) pilots = v;
-        else if ((v = val("--bits-ring"))) bits_ring = v;
-        else if ((v = val("--bits-slots"))) bits_slots = atoi(v);
-        else if ((v = val("--lanes"))) n_lanes = atoi(v);
-        else if ((v = val("--batch"))) batch = atoi(v);
-        else if (std::strcmp(argv[i], "--no-output") == 0) write_out = false;
-        else {
-            fprintf(stderr, "unknown argument %s\n", argv[i]);
-            return 2;
-        }
+};
+struct Result {
+    int rc = 0;
+    double seconds = 0;
+    std::string plan;
+};
+
+// run this thread on the cores next to GPU `gpu` (sysfs local_cpulist of its PCI device); best effort
+static void pin_thread_near_gpu(int gpu)
+{
+    char bdf[64] = "";
+    if (lsmrc_device_pci_bus_id(gpu, bdf, sizeof bdf) != LSMRC_OK) return;
+    for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+    std::ifstream in(std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist");
+    std::string list;
+    if (!in || !std::getline(in, list)) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    const char* p = list.c_str();
+    while (*p) {
+        char* e;
+        long lo = strtol(p, &e, 10), hi = lo;
+        if (e == p) break;
+        if (*e == '-') hi = strtol(e + 1, &e, 10);
+        for (long c = lo; c <= hi && c < CPU_SETSIZE; ++c, ++n) CPU_SET((int)c, &set);
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',' ) break;
     }
-    // default: 3 submissions in flight for large frames (copy-bound), 4 for frames below 1 MB (launch-latency bound)
-    if (n_lanes < 1 || n_lanes > 64) n_lanes = ((size_t)syms * rows * (cols + cp) * sizeof(complexF) < (1u << 20)) ? 4 : 3;
-    const bool small = (size_t)syms * rows * (cols + cp) * sizeof(complexF) < (1u << 20);
-    if (batch < 1 || batch > 64) batch = small ? 16 : 1;
-    if (ring <= 0) ring = (n_lanes * batch + 1) * syms + 1;
-    if (ring < syms + 1) {
-        fprintf(stderr, "the ring (%d slots) must hold at least one frame of %d slots plus one\n", ring, syms);
-        return 2;
-    }
-    gpuLS ls(rows, cols, cp, syms, qam, ring, shm, 0, 0, n_lanes, batch);
-    if (lsmrc_set_pilot_file(ls.handle, pilots.c_str()) < 0) {
+    if (n > 0) sched_setaffinity(0, sizeof set, &set);
+}
+
+// One ring -> one GPU: frames are taken whole out of the pinned ring `shm` and rotated over the handle's lanes.
+static void run_stream(const Args& a, int gpu, const std::string& shm, const std::string& suffix, Result* res)
+{
+    const int rows = a.rows, cols = a.cols, cp = a.cp, syms = a.syms, qam = a.qam, n_lanes = a.n_lanes, batch = a.batch, ring = a.ring,
+              frames = a.frames;
+    if (a.gpus > 1) pin_thread_near_gpu(gpu);
+    gpuLS ls(rows, cols, cp, syms, qam, ring, shm, 0, gpu, n_lanes, batch);
+    if (lsmrc_set_pilot_file(ls.handle, a.pilots.c_str()) < 0) {
         fprintf(stderr, "pilot: %s\n", lsmrc_last_error(ls.handle));
-        return 1;
+        res->rc = 1;
+        return;
     }
     const int K = cols - 1;
     const size_t comb_bytes = (size_t)(syms - 1) * K * sizeof(cuFloatComplex);
     const size_t bits_bytes = (size_t)(syms - 1) * lsmrc_bits_row_bytes(cols, qam);
-    std::ofstream out, outb;
-    if (write_out) {
-        out.open("Output_gpu.dat", std::ofstream::binary | std::ofstream::trunc);
-        outb.open("Bits_gpu.dat", std::ofstream::binary | std::ofstream::trunc);
+    std::ofstream out, outb, trace;
+    if (a.write_out) {
+        out.open(("Output_gpu" + suffix + ".dat").c_str(), std::ofstream::binary | std::ofstream::trunc);
+        outb.open(("Bits_gpu" + suffix + ".dat").c_str(), std::ofstream::binary | std::ofstream::trunc);
     }
-    ShMemBitsBuff* ret = bits_ring.empty() ? nullptr : new ShMemBitsBuff(bits_ring, 1, bits_bytes, bits_slots);
-    std::vector<int> lane_n((size_t)n_lanes, 0);  // frames of the submission in flight on each lane
+    if (!a.trace.empty()) {
+        trace.open((a.trace + suffix).c_str(), std::ofstream::trunc);
+        trace << "submission,lane,frames,t_enqueued_ms,t_h2d_done_ms,t_kernels_done_ms,t_results_on_host_ms\n";
+    }
+    ShMemBitsBuff* ret = a.bits_ring.empty() ? nullptr : new ShMemBitsBuff(a.bits_ring + suffix, 1, bits_bytes, a.bits_slots);
+    std::vector<int> lane_n((size_t)n_lanes, 0);    // frames of the submission in flight on each lane
+    std::vector<int> lane_sub((size_t)n_lanes, 0);  // ... and its running number
     auto collect = [&](int lane) {
         const void *comb = nullptr, *bits = nullptr;
         if (lsmrc_ring_wait(ls.handle, lane, &comb, &bits, nullptr) < 0) {
@@ -86,7 +99,12 @@ int main(int argc, char** argv)
             exit(1);
         }
         const int n = lane_n[(size_t)lane];
-        if (write_out) {
+        if (trace.is_open()) {
+            float t[4];
+            if (lsmrc_ring_trace(ls.handle, lane, t) == LSMRC_OK)
+                trace << lane_sub[(size_t)lane] << ',' << lane << ',' << n << ',' << t[0] << ',' << t[1] << ',' << t[2] << ',' << t[3] << '\n';
+        }
+        if (a.write_out) {
             out.write(static_cast<const char*>(comb), (std::streamsize)(comb_bytes * n));
             outb.write(static_cast<const char*>(bits), (std::streamsize)(bits_bytes * n));
         }
@@ -140,9 +158,11 @@ int main(int argc, char** argv)
         ls.buffPtr->waitFrameAt(unreleased_frames * syms, nb * syms, &first, &n_first, &second);
         if (lsmrc_ring_submit_frames(ls.handle, lane, first, n_first, second, nb) < 0) {
             fprintf(stderr, "ring_submit: %s\n", lsmrc_last_error(ls.handle));
-            return 1;
+            res->rc = 1;
+            return;
         }
         lane_n[(size_t)lane] = nb;
+        lane_sub[(size_t)lane] = sub;
         unreleased_frames += nb;
         ++unreleased_subs;
         ++busy;
@@ -151,12 +171,75 @@ int main(int argc, char** argv)
     }
     while (unreleased_subs > 0) release_oldest(true);
     for (int i = sub - busy; i < sub; ++i) collect(i % n_lanes);
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    const double samples = (double)frames * syms * rows * (cols + cp);
+    res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     delete ret;  // unlinks the name; a reader that is still draining keeps its mapping
     char plan[256] = "";
     lsmrc_describe_plan(ls.handle, plan, sizeof plan);
-    printf("{\"frames\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f, \"plan\": \"%s\"}\n",
-           frames, dt, frames / dt, samples / dt, samples * 8.0 / dt / 1e9, plan);
+    res->plan = plan;
+}
+
+int main(int argc, char** argv)
+{
+    Args a;
+    for (int i = 1; i < argc; ++i) {
+        auto val = [&](const char* name) -> const char* {
+            if (std::strcmp(argv[i], name) == 0 && i + 1 < argc) return argv[++i];
+            return nullptr;
+        };
+        const char* v;
+        if ((v = val("--rows"))) a.rows = atoi(v);
+        else if ((v = val("--cols"))) a.cols = atoi(v);
+        else if ((v = val("--prefix"))) a.cp = atoi(v);
+        else if ((v = val("--syms"))) a.syms = atoi(v);
+        else if ((v = val("--qam"))) a.qam = atoi(v);
+        else if ((v = val("--ring"))) a.ring = atoi(v);
+        else if ((v = val("--frames"))) a.frames = atoi(v);
+        else if ((v = val("--shm"))) a.shm = v;
+        else if ((v = val("--pilots"))) a.pilots = v;
+        else if ((v = val("--bits-ring"))) a.bits_ring = v;
+        else if ((v = val("--bits-slots"))) a.bits_slots = atoi(v);
+        else if ((v = val("--lanes"))) a.n_lanes = atoi(v);
+        else if ((v = val("--batch"))) a.batch = atoi(v);
+        else if ((v = val("--gpus"))) a.gpus = atoi(v);
+        else if ((v = val("--trace"))) a.trace = v;
+        else if (std::strcmp(argv[i], "--no-output") == 0) a.write_out = false;
+        else {
+            fprintf(stderr, "unknown argument %s\n", argv[i]);
+            return 2;
+        }
+    }
+    // default: 3 submissions in flight for large frames (copy-bound), 4 for frames below 1 MB (launch-latency bound)
+    const bool small = (size_t)a.syms * a.rows * (a.cols + a.cp) * sizeof(complexF) < (1u << 20);
+    if (a.n_lanes < 1 || a.n_lanes > 64) a.n_lanes = small ? 4 : 3;
+    if (a.batch < 1 || a.batch > 64) a.batch = small ? 16 : 1;
+    if (a.ring <= 0) a.ring = (a.n_lanes * a.batch + 1) * a.syms + 1;
+    if (a.ring < a.syms + 1) {
+        fprintf(stderr, "the ring (%d slots) must hold at least one frame of %d slots plus one\n", a.ring, a.syms);
+        return 2;
+    }
+    if (a.gpus < 1 || a.gpus > 64) {
+        fprintf(stderr, "--gpus must be in 1..64\n");
+        return 2;
+    }
+    // --gpus G: G rings (<shm>_0 .. <shm>_{G-1}), one worker thread and one receiver handle per GPU, every worker on
+    // the cores next to its GPU; `frames` frames per GPU.  Output files and the trace get the suffix _<g>.
+    std::vector<Result> res((size_t)a.gpus);
+    if (a.gpus == 1) {
+        run_stream(a, 0, a.shm, "", &res[0]);
+    } else {
+        std::vector<std::thread> workers;
+        for (int g = 0; g < a.gpus; ++g)
+            workers.emplace_back([&a, &res, g] { run_stream(a, g, a.shm + "_" + std::to_string(g), "_" + std::to_string(g), &res[(size_t)g]); });
+        for (auto& w : workers) w.join();
+    }
+    double dt = 0;
+    for (const Result& r : res) {
+        if (r.rc != 0) return r.rc;
+        if (r.seconds > dt) dt = r.seconds;  // the slowest GPU
+    }
+    const double total_frames = (double)a.frames * a.gpus;
+    const double samples = total_frames * a.syms * a.rows * (a.cols + a.cp);
+    printf("{\"frames\": %.0f, \"gpus\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f, \"plan\": \"%s\"}\n",
+           total_frames, a.gpus, dt, total_frames / dt, samples / dt, samples * 8.0 / dt / 1e9, res[0].plan.c_str());
     return 0;
 }

@@ -78,7 +78,11 @@ const char *lsmrc_error_name(int code);
 /* ---- geometry helpers -------------------------------------------------------------- */
 size_t lsmrc_bits_row_bytes(int fft_size, int qam_bits);         /* ceil((N-1)*b/8) */
 size_t lsmrc_rx_frame_elems(const lsmrc_config *cfg);            /* S*A*(N+C) complex */
-int lsmrc_supported_fft_size(int fft_size);                      /* 1 if a plan is built */
+int lsmrc_supported_fft_size(int fft_size);
+/* multi-GPU hosts (one handle and one worker thread per GPU; gpuLS_main.cu:69 pins the reference to device 0):
+ * number of CUDA devices, and "dddd:bb:dd.f" of one of them (to find its NUMA node under /sys/bus/pci/devices) */
+int lsmrc_device_count(void);
+int lsmrc_device_pci_bus_id(int device, char *buf, size_t buf_len);                      /* 1 if a plan is built */
 
 /* ---- pilot (replaces gpuLS::matrix_readX, gpuLS.cu:53-86, and copyPilotToGPU :88-106) - */
 /* pilot_asc: K complex64 in ascending-frequency (file) order; rolled to bin order inside. */
@@ -154,6 +158,11 @@ int lsmrc_ring_wait(lsmrc_handle h, int lane, const void **combined, const void 
 int lsmrc_ring_copy_done(lsmrc_handle h, int lane);
 /* non-blocking form: 1 when the slots of the frame last submitted to `lane` may be reused, 0 when not yet */
 int lsmrc_ring_copy_query(lsmrc_handle h, int lane);
+/* Timeline of the submission last collected from `lane` (after lsmrc_ring_wait), CUDA-event milliseconds since the
+ * handle's first ring submission: ms4[0] submission enqueued (H2D starts when the lane's stream reaches it), [1] H2D
+ * finished / slots free, [2] kernels finished, [3] results on the host.  Evidence for the overlap of the three phases
+ * across lanes (replaces the clock() timers of ShMemSymBuff_gpu.hpp:373-445). */
+int lsmrc_ring_trace(lsmrc_handle h, int lane, float *ms4);
 
 /* ---- stand-alone steps: the individually callable kernel wrappers of gpuLS.cuh:87-99.  The fused
  *      entry points above never go through them; they produce the same intermediate tensors the

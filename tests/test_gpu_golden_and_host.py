@@ -247,3 +247,68 @@ def test_reference_gpu_driver_unmodified_runs_on_the_facade(ofdm, oracle, host_b
     times = np.fromfile(tmp_path / "time_gpu.dat", np.float32)
     assert times.shape == (5,) and np.isfinite(times).all() and (times >= 0).all(), times
     assert "ChanEst" in r.stdout                      # printTimes(true) table, ShMemSymBuff_gpu.hpp:153-162
+
+
+def test_stream_main_full_config3_with_trace(ofdm, oracle, host_bins, tmp_path):
+    """BASELINE config c3 at its full shape (128 antennas x 2048 points x 14 symbols, 31 MB per frame) through the ring
+    on three lanes, with the per-submission timeline: results equal the oracle's, and the H2D copy of a frame runs
+    while an earlier frame is still in the kernels / on its way back (the overlap north_star asks for)."""
+    A, N, C, S, b, F = 128, 2048, 144, 14, 4, 9
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=15.0, seed=1237)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    comb, bits, out = _run_ring(host_bins, tmp_path, "stream_main", ["--lanes", "3", "--trace", str(tmp_path / "trace.csv")],
+                                d, A, N, C, S, b, F, 4 * S + 1)
+    assert_close(comb, ref["combined"], "stream_main combined (full c3)")
+    assert np.array_equal(bits, ref["bits"])
+    t = np.loadtxt(tmp_path / "trace.csv", delimiter=",", skiprows=1)
+    assert t.shape == (F, 7)
+    t = t[np.argsort(t[:, 0])]
+    enq, h2d, ker, done = t[:, 3], t[:, 4], t[:, 5], t[:, 6]
+    assert (enq <= h2d).all() and (h2d <= ker).all() and (ker <= done).all()
+    # submission i+1's copy starts before submission i has delivered its results, for most i
+    overlapped = int((enq[1:] < done[:-1]).sum())
+    assert overlapped >= (F - 1) // 2, (overlapped, t)
+
+
+def test_stream_main_two_gpus_one_worker_per_gpu(ofdm, oracle, host_bins, tmp_path):
+    """stream_main --gpus 2: one ring, one worker thread and one receiver handle per GPU inside one process
+    (SURVEY 8e); each GPU's output equals the oracle on its own frames."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    A, N, C, S, b, F = 8, 1024, 64, 6, 4, 5
+    shm = "/lsmrc_" + uuid.uuid4().hex[:8]
+    ds, feeders = [], []
+    pil = None
+    try:
+        for g in range(2):
+            d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=15.0, seed=500 + g, pilot_asc=pil)
+            pil = d["pilot_asc"]
+            ds.append(d)
+            f = tmp_path / f"rx_{g}.bin"
+            d["rx"].tofile(f)
+            feeders.append(subprocess.Popen([os.path.join(host_bins, "ring_feeder"), "--file", str(f), "--frames", str(F), "--rows", str(A),
+                                             "--cols", str(N), "--prefix", str(C), "--syms", str(S), "--ring", str(4 * S + 1),
+                                             "--shm", f"{shm}_{g}"]))
+        pil.tofile(tmp_path / "Pilots.dat")
+        r = subprocess.run([os.path.join(host_bins, "stream_main"), "--gpus", "2", "--qam", str(b), "--frames", str(F), "--pilots",
+                            str(tmp_path / "Pilots.dat"), "--rows", str(A), "--cols", str(N), "--prefix", str(C), "--syms", str(S),
+                            "--ring", str(4 * S + 1), "--shm", shm], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        for f in feeders:
+            f.wait(timeout=60)
+    finally:
+        for f in feeders:
+            if f.poll() is None:
+                f.kill()
+        for g in range(2):
+            if os.path.exists(f"/dev/shm{shm}_{g}"):
+                os.unlink(f"/dev/shm{shm}_{g}")
+    assert '"gpus": 2' in r.stdout
+    for g in range(2):
+        ref = oracle.demod_frames(ds[g]["rx"], pil, b, C)
+        comb = np.fromfile(tmp_path / f"Output_gpu_{g}.dat", np.complex64).reshape(F, S - 1, N - 1)
+        bits = np.fromfile(tmp_path / f"Bits_gpu_{g}.dat", np.uint8).reshape(F, S - 1, -1)
+        assert_close(comb, ref["combined"], f"GPU {g} combined")
+        assert np.array_equal(bits, ref["bits"])

@@ -104,3 +104,49 @@ def test_gpu_noise_estimate_and_llrs_from_combined(ofdm, oracle, dims):
     want = np.stack([oracle.soft_demap(ref["combined"][f:f + 1], ref["hsqrd"][f:f + 1], b, float(np.float32(want_nv[f])))[0]
                      for f in range(F)])
     assert_close(llr.cpu().numpy(), want, "LLRs from combined", tol=5e-5)
+
+
+@pytest.mark.parametrize("b", [2, 4, 6])
+def test_llrs_against_brute_force_max_log_over_the_constellation(oracle, ofdm, b):
+    """Independent pin of the soft demapper (the reference has none): brute-force max-log LLRs in float64,
+        LLR_j = rho * ( min_{s: bit j = 1} |y - s|^2  -  min_{s: bit j = 0} |y - s|^2 ),   rho = sum|H|^2 / noise_var,
+    over all 2^b points of the TS 38.211 constellation (ofdm.synth.qam_map_indices, the transmit-side mapper).
+    The shipped form is the usual piecewise-linear simplification; where the two coincide they must agree to rounding:
+      * QPSK: everywhere;
+      * amplitude bits of 16-QAM (bits 2, 3) and the last amplitude bits of 64-QAM (bits 4, 5): everywhere / inside the
+        decision regions that do not touch the outermost level;
+      * sign bits (0, 1): for |u| <= 2a, i.e. while the nearest point of EITHER sign is an innermost one.
+    Outside those regions the simplification keeps the inner segment's slope: same sign, smaller magnitude -- it
+    under-states the confidence of symbols far outside the constellation and never flips a decision."""
+    rng = np.random.default_rng(100 + b)
+    K = 4001
+    a = {2: 1 / np.sqrt(2), 4: 1 / np.sqrt(10), 6: 1 / np.sqrt(42)}[b]
+    sym = (1.2 * (rng.standard_normal((1, 1, K)) + 1j * rng.standard_normal((1, 1, K))) / np.sqrt(2)).astype(np.complex64)
+    e = (0.5 + 4 * rng.random((1, K))).astype(np.float32)
+    nv = 0.3
+    got = oracle.soft_demap(sym, e, b, noise_var=nv)[0, 0].astype(np.float64)          # [K][b]
+    pts = ofdm.synth.qam_map_indices(np.arange(1 << b), b)                              # [2^b]
+    y = sym[0, 0].astype(np.complex128)
+    d2 = np.abs(y[:, None] - pts[None, :]) ** 2                                         # [K][2^b]
+    # sum|H|^2 is indexed by FFT bin, the symbols are in ascending frequency: position i <-> bin index (i + (K-1)/2) mod K
+    rho = np.roll(e[0].astype(np.float64), -((K - 1) // 2)) / nv
+    exact = np.empty((K, b))
+    for j in range(b):
+        one = ((np.arange(1 << b) >> j) & 1).astype(bool)
+        exact[:, j] = rho * (d2[:, one].min(1) - d2[:, ~one].min(1))
+    u = np.stack([y.real, y.imag] * (b // 2), axis=1)                                   # axis value bit j looks at
+    au = np.abs(u)
+    same = np.zeros((K, b), bool)
+    same[:, 0:2] = au[:, 0:2] <= 2 * a if b > 2 else True
+    if b == 4:
+        same[:, 2:4] = True
+    if b == 6:
+        same[:, 2:4] = (au[:, 2:4] >= 2 * a) & (au[:, 2:4] <= 6 * a)                    # between the two middle levels' outer neighbours
+        same[:, 4:6] = au[:, 4:6] <= 8 * a
+    scale = np.abs(exact).max()
+    assert same.mean() > 0.5
+    assert np.abs(got - exact)[same].max() <= 2e-6 * scale, np.abs(got - exact)[same].max() / scale
+    # elsewhere: same decision, never over-confident
+    nz = np.abs(exact) > 2e-6 * scale
+    assert np.array_equal(np.sign(got[nz]), np.sign(exact[nz]))
+    assert (np.abs(got) <= np.abs(exact) + 2e-6 * scale).all()   # (absolute: fp32 cancellation next to a threshold)

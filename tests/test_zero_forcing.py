@@ -82,3 +82,37 @@ def test_gpu_zero_forcing_counts_singular_subcarriers(ofdm):
     h = torch.view_as_complex(dh).cpu().numpy()
     assert bad == 1 and not h[4].any()
     assert np.isfinite(h[[0, 1, 2, 3, 5, 6, 7, 8]].view(np.float32)).all()
+
+
+@pytest.mark.parametrize("U,A,K", [(2, 4, 63), (4, 16, 255), (4, 64, 1023), (8, 32, 64)])
+def test_oracle_equals_the_reference_call_sequence_on_real_lapack(oracle, U, A, K):
+    """Pin for this row: createZeroForcingMatrix / multiplyWithChannelInv (cpuLS.hpp:415-463) call cblas_cgemm,
+    cgetrf_, cgetri_ and cblas_cgemv in complex64.  CBLAS/LAPACK headers are absent from this image, so the reference
+    function cannot be compiled -- but scipy ships the very same routines (OpenBLAS): the reference's call sequence is
+    replayed here on them, per subcarrier, in complex64, and the oracle (plain loops + Gauss-Jordan in double) must agree
+    to single-precision rounding amplified by the conditioning of the Gram matrix."""
+    from scipy.linalg import blas, lapack
+
+    X = _channels(U, A, K, 11)
+    xd = _channels(1, U, K, 12)[0]
+    got_h, bad = oracle.zf_create(X)
+    got_hx = oracle.zf_apply(got_h, xd)
+    assert bad == 0
+    one = np.complex64(1)
+    want_h = np.empty((K, U, A), np.complex64)
+    want_hx = np.empty((A, K), np.complex64)
+    worst = 0.0
+    for k in range(K):
+        Xk = np.asfortranarray(X[:, :, k])                       # rotCube: users x rows, column-major, ld = users
+        G = blas.cgemm(one, Xk, Xk, trans_b=2)                   # Xk * Xk^H                 (cpuLS.hpp:437)
+        lu, piv, info = lapack.cgetrf(G)                         #                            (:438)
+        assert info == 0
+        Ginv, info = lapack.cgetri(lu, piv)                      #                            (:439)
+        assert info == 0
+        Hk = blas.cgemm(one, Xk, Ginv, trans_a=2)                # Xk^H * inv, rows x users   (:440)
+        want_h[k] = Hk.T                                         # stored column-major with ld = rows: H[k][u][a]
+        want_hx[:, k] = blas.cgemv(one, Hk, xd[:, k])            # multiplyWithChannelInv     (:460)
+        worst = max(worst, np.linalg.cond(G.astype(np.complex128)))
+    tol = 3e-6 * worst
+    assert np.abs(got_h - want_h).max() <= tol * np.abs(want_h).max(), (np.abs(got_h - want_h).max() / np.abs(want_h).max(), worst)
+    assert np.abs(got_hx - want_hx).max() <= tol * np.abs(want_hx).max()
