@@ -36,7 +36,9 @@ struct Args {
 };
 struct Result {
     int rc = 0;
-    double seconds = 0;
+    double seconds = 0;         // from the start of the consume loop (includes waiting for the producer's first frame
+                                // and the first-use allocation of the lanes)
+    double steady_seconds = 0;  // from the first submission
     std::string plan;
 };
 
@@ -116,6 +118,7 @@ static void run_stream(const Args& a, int gpu, const std::string& shm, const std
         }
     };
     const auto t0 = std::chrono::steady_clock::now();
+    auto t_first = t0;
     // Up to n_lanes submissions (of up to `batch` frames each) are in flight.  Two things trail them, both in order:
     // the slots of a submission go back to the producer as soon as the GPU no longer reads them (its H2D copy, or
     // the in-place kernel, has finished -- polled, so the producer refills while later stages still run), and a
@@ -156,6 +159,7 @@ static void run_stream(const Args& a, int gpu, const std::string& shm, const std
         const complexF *first = nullptr, *second = nullptr;
         int n_first = 0;
         ls.buffPtr->waitFrameAt(unreleased_frames * syms, nb * syms, &first, &n_first, &second);
+        if (sub == 0) t_first = std::chrono::steady_clock::now();
         if (lsmrc_ring_submit_frames(ls.handle, lane, first, n_first, second, nb) < 0) {
             fprintf(stderr, "ring_submit: %s\n", lsmrc_last_error(ls.handle));
             res->rc = 1;
@@ -172,6 +176,7 @@ static void run_stream(const Args& a, int gpu, const std::string& shm, const std
     while (unreleased_subs > 0) release_oldest(true);
     for (int i = sub - busy; i < sub; ++i) collect(i % n_lanes);
     res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    res->steady_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_first).count();
     delete ret;  // unlinks the name; a reader that is still draining keeps its mapping
     char plan[256] = "";
     lsmrc_describe_plan(ls.handle, plan, sizeof plan);
@@ -232,14 +237,16 @@ int main(int argc, char** argv)
             workers.emplace_back([&a, &res, g] { run_stream(a, g, a.shm + "_" + std::to_string(g), "_" + std::to_string(g), &res[(size_t)g]); });
         for (auto& w : workers) w.join();
     }
-    double dt = 0;
+    double dt = 0, dts = 0;
     for (const Result& r : res) {
         if (r.rc != 0) return r.rc;
         if (r.seconds > dt) dt = r.seconds;  // the slowest GPU
+        if (r.steady_seconds > dts) dts = r.steady_seconds;
     }
     const double total_frames = (double)a.frames * a.gpus;
     const double samples = total_frames * a.syms * a.rows * (a.cols + a.cp);
-    printf("{\"frames\": %.0f, \"gpus\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f, \"plan\": \"%s\"}\n",
-           total_frames, a.gpus, dt, total_frames / dt, samples / dt, samples * 8.0 / dt / 1e9, res[0].plan.c_str());
+    printf("{\"frames\": %.0f, \"gpus\": %d, \"seconds\": %.6f, \"frames_per_s\": %.2f, \"antenna_samples_per_s\": %.4e, \"h2d_gbs\": %.3f, "
+           "\"seconds_from_first_submission\": %.6f, \"h2d_gbs_from_first_submission\": %.3f, \"plan\": \"%s\"}\n",
+           total_frames, a.gpus, dt, total_frames / dt, samples / dt, samples * 8.0 / dt / 1e9, dts, samples * 8.0 / dts / 1e9, res[0].plan.c_str());
     return 0;
 }
