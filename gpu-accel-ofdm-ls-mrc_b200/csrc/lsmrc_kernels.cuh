@@ -44,13 +44,6 @@
 
 #include "fft_radix.cuh"
 
-// development A/B switch of lsmrc_data_sh: antenna rows by bulk copy into the tile (1) or by plain loads (0)
-#ifndef LSMRC_SH_XMODE
-#define LSMRC_SH_XMODE 1
-#endif
-#ifndef LSMRC_SH_HMODE  // channel rows staged in shared memory by bulk copy (1) or loaded straight from L2 (0)
-#define LSMRC_SH_HMODE 1
-#endif
 constexpr int kHStages = 3;  // depth of the Hconj ring (rows)
 constexpr int kTwChunk = 4;  // inter-stage twiddles fetched this many at a time, one chunk ahead of their use
 
@@ -523,9 +516,6 @@ __device__ __forceinline__ void sh_radix_batch(const float2 (&keep)[JB], const f
         const bool odd = (q & 1) != 0;
         const float s0 = odd ? -1.f : 1.f;
         const float2 sp = make_float2(s0, s0), sm = make_float2(-s0, -s0);
-        // odd lanes: p + i*r2 = p + swp(r2) * (-1, 1)
-        const float2 kp = odd ? make_float2(-1.f, 1.f) : make_float2(1.f, 1.f);
-        const float2 km = make_float2(-kp.x, -kp.y);
         float2 r1[JB], pp[JB], mm[JB], r2[JB];
 #pragma unroll
         for (int i = 0; i < JB; ++i) {
@@ -544,9 +534,11 @@ __device__ __forceinline__ void sh_radix_batch(const float2 (&keep)[JB], const f
         }
 #pragma unroll
         for (int i = 0; i < JB; ++i) {
-            const float2 rr = odd ? swp(r2[i]) : r2[i];
-            A[i] = __ffma2_rn(rr, kp, pp[i]);
-            B[i] = __ffma2_rn(rr, km, pp[i]);
+            // odd lanes: i*r2 = (-r2.y, r2.x); the negation rides on the select, so both kinds of lane finish with
+            // the same two packed adds and no per-lane constant pair has to be kept (or rebuilt) in registers
+            const float2 rr = make_float2(odd ? -r2[i].y : r2[i].x, odd ? r2[i].x : r2[i].y);
+            A[i] = cadd(pp[i], rr);
+            B[i] = csub(pp[i], rr);
         }
     }
 }
@@ -1543,7 +1535,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
     row.readers = &s_readers[team];
     row.tmem = tmem;
     row.x_phase = 0;
-    row.x_tma = p.x_tma != 0 && LSMRC_SH_XMODE != 0;
+    row.x_tma = p.x_tma != 0;
     row.t = t, row.lane = lane, row.wt = wt, row.team = team, row.q = q, row.k1 = k1;
     uint32_t h_phase = 0;
 
@@ -1580,33 +1572,22 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
             float2 v[32];
             sh_row_front<PL>(row, v, x_row, a + 1 < p.n_ant ? x_row + p.ant_stride : nullptr, [&]() {
                 // every warp of the team is past the previous antenna: its channel row may be replaced
-#if LSMRC_SH_HMODE
                 if (t == 0) {
                     mbar_expect_tx(&bar_h[team], ROW_BYTES);
                     bulk_g2s_hint(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team], l2_policy_evict_last());
                 }
-#endif
             });
             // ---- twiddle W_T^(q*k2), radix-SH across the lanes, multiply-accumulate with conj(H)
             constexpr int JB = kShBatch;
-#if LSMRC_SH_HMODE
             pin_values(v);  // the stage-2 transform stays ahead of the wait: it is the time the channel row has to land
             mbar_wait(&bar_h[team], h_phase);
             h_phase ^= 1u;
-#else
-            const float2* hw_row = hw_frame + (long long)a * N + t;
-#endif
 #pragma unroll
             for (int c = 0; c < 16 / JB; ++c) {
                 float2 tw[2 * JB], h[2 * JB];
                 tmem_load8(tmem, 64 + 16 * c, tw);
-#if LSMRC_SH_HMODE
 #pragma unroll
                 for (int i = 0; i < 2 * JB; ++i) h[i] = lds_volatile(hbuf + (2 * JB * c + i) * T + t);
-#else
-#pragma unroll
-                for (int i = 0; i < 2 * JB; ++i) h[i] = __ldg(hw_row + (2 * JB * c + i) * T);
-#endif
                 asm volatile("" ::: "memory");
                 float2 keep[JB], send[JB], A[JB], B[JB];
 #pragma unroll
@@ -1691,7 +1672,7 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_pilot_sh(const Kernel
     row.readers = &s_readers[team];
     row.tmem = tmem;
     row.x_phase = 0;
-    row.x_tma = p.x_tma != 0 && LSMRC_SH_XMODE != 0;
+    row.x_tma = p.x_tma != 0;
     row.t = t, row.lane = lane, row.wt = wt, row.team = team, row.q = q, row.k1 = k1;
 
     const int per_iter = p.n_groups * TEAMS;
