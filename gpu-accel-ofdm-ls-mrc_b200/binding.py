@@ -37,6 +37,7 @@ ABI = {
     "lsmrc_get_channel": (c_int, [c_void_p, c_void_p, c_void_p]),
     "lsmrc_get_channel_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "lsmrc_ring_submit_frame": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
+    "lsmrc_ring_prepare": (c_int, [c_void_p]),
     "lsmrc_ring_submit_split": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "lsmrc_ring_wait": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "lsmrc_ring_copy_done": (c_int, [c_void_p, c_int]),

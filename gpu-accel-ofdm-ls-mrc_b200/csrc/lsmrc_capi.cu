@@ -796,6 +796,13 @@ struct ScopedPin {
     }
 };
 
+// whether the H2D copies of whole slots leave the cyclic prefix on the host (strided copy; rows long enough for the copy engine)
+bool strip_cp_on_h2d(const lsmrc_ctx* h)
+{
+    const lsmrc_config& c = h->cfg;
+    return h->h2d_strip_cp && c.cp_len > 0 && (size_t)c.fft_size * sizeof(float2) >= h->h2d_strip_min_row;
+}
+
 int alloc_lane(lsmrc_ctx* h, Lane& L)
 {
     const lsmrc_config& c = h->cfg;
@@ -1298,7 +1305,7 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     pin_bt.pin(h_bits, bt_fb * n_frames);
 
     // strided H2D that skips the cyclic prefix: worth it when rows are long enough for the copy engine
-    const bool strip_cp = h->h2d_strip_cp && c.cp_len > 0 && (size_t)c.fft_size * sizeof(float2) >= h->h2d_strip_min_row;
+    const bool strip_cp = strip_cp_on_h2d(h);
     int chunk_idx = 0;
     for (int f0 = 0; f0 < n_frames; f0 += c.max_frames, ++chunk_idx) {
         const int nf = (n_frames - f0 < c.max_frames) ? (n_frames - f0) : c.max_frames;
@@ -1416,12 +1423,32 @@ static cudaError_t ring_mark_start(lsmrc_ctx* h, Lane& L)
     return cudaEventRecord(L.t_start, L.st);
 }
 
-static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L, int n_frames)
+// H2D of n_slots consecutive ring slots into the lane's staging tensor starting at slot position `at`: the slots are one
+// uniform [n_slots * A][N + C] array, so leaving the prefix behind is a single strided copy.
+static int ring_copy_slots(lsmrc_ctx* h, Lane& L, const void* h_slots, int at, int n_slots, bool strip)
+{
+    const lsmrc_config& c = h->cfg;
+    if (n_slots <= 0) return LSMRC_OK;
+    if (strip) {
+        const size_t row = (size_t)c.fft_size * sizeof(float2), pitch = (size_t)(c.fft_size + c.cp_len) * sizeof(float2);
+        CK(h, cudaMemcpy2DAsync(reinterpret_cast<char*>(L.d_rx) + (size_t)at * c.n_ant * row, row,
+                                static_cast<const char*>(h_slots) + (size_t)c.cp_len * sizeof(float2), pitch, row, (size_t)n_slots * c.n_ant,
+                                cudaMemcpyHostToDevice, L.st));
+    } else {
+        const size_t slot_bytes = h->slot_elems * sizeof(float2);
+        CK(h, cudaMemcpyAsync(reinterpret_cast<char*>(L.d_rx) + (size_t)at * slot_bytes, h_slots, slot_bytes * n_slots, cudaMemcpyHostToDevice, L.st));
+    }
+    return LSMRC_OK;
+}
+
+static int ring_enqueue_compute(lsmrc_ctx* h, Lane& L, int n_frames, bool dense = false)
 {
     const lsmrc_config& c = h->cfg;
     const size_t nd = (size_t)(c.n_sym - 1);
     CK(h, cudaEventRecord(L.copied, L.st));
-    int rc = launch_frames(h, L.st, L.d_rx, n_frames, L.ch, L.d_hconj, nullptr, L.d_comb, L.d_bits, false);
+    RxLayout dense_lay{};
+    dense_lay.dense = true;
+    int rc = launch_frames(h, L.st, L.d_rx, n_frames, L.ch, L.d_hconj, nullptr, L.d_comb, L.d_bits, false, dense ? &dense_lay : nullptr);
     if (rc != LSMRC_OK) return rc;
     CK(h, cudaEventRecord(L.t_kernels, L.st));
     if (nd > 0) {
@@ -1473,6 +1500,13 @@ static int ring_try_in_place(lsmrc_ctx* h, Lane& L, const void* h_first, int n_f
     return 1;
 }
 
+int lsmrc_ring_prepare(lsmrc_handle h)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    CK(h, cudaSetDevice(h->cfg.device));
+    return ensure_lanes(h);
+}
+
 int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_t slot_stride_bytes)
 {
     if (!h || !h_slots) return fail(h, LSMRC_ERR_INVALID, "null argument");
@@ -1487,7 +1521,9 @@ int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void* h_slots, size_
     CK(h, ring_mark_start(h, L));
     if ((rc = ring_try_in_place(h, L, h_slots, h->cfg.n_sym, nullptr, slot_stride_bytes)) != 0) return rc < 0 ? rc : LSMRC_OK;
     if (slot_stride_bytes == slot_bytes) {
-        CK(h, cudaMemcpyAsync(L.d_rx, h_slots, slot_bytes * h->cfg.n_sym, cudaMemcpyHostToDevice, L.st));
+        const bool strip = strip_cp_on_h2d(h);
+        if ((rc = ring_copy_slots(h, L, h_slots, 0, h->cfg.n_sym, strip)) != LSMRC_OK) return rc;
+        return ring_enqueue_compute(h, L, 1, strip);
     } else {
         CK(h, cudaMemcpy2DAsync(L.d_rx, slot_bytes, h_slots, slot_stride_bytes, slot_bytes, (size_t)h->cfg.n_sym,
                                 cudaMemcpyHostToDevice, L.st));
@@ -1510,11 +1546,10 @@ int lsmrc_ring_submit_frames(lsmrc_handle h, int lane, const void* h_first, int 
     const size_t slot_bytes = h->slot_elems * sizeof(float2);
     CK(h, ring_mark_start(h, L));
     if (n_first > 0 && (rc = ring_try_in_place(h, L, h_first, n_first, h_second, slot_bytes, n_frames)) != 0) return rc < 0 ? rc : LSMRC_OK;
-    if (n_first > 0) CK(h, cudaMemcpyAsync(L.d_rx, h_first, slot_bytes * n_first, cudaMemcpyHostToDevice, L.st));
-    if (n_first < n_slots)
-        CK(h, cudaMemcpyAsync(reinterpret_cast<char*>(L.d_rx) + slot_bytes * n_first, h_second, slot_bytes * (n_slots - n_first),
-                              cudaMemcpyHostToDevice, L.st));
-    return ring_enqueue_compute(h, L, n_frames);
+    const bool strip = strip_cp_on_h2d(h);  // the cyclic prefix is never used: leave it in the ring (C/(N+C) of the PCIe bytes)
+    if ((rc = ring_copy_slots(h, L, h_first, 0, n_first, strip)) != LSMRC_OK) return rc;
+    if ((rc = ring_copy_slots(h, L, h_second, n_first, n_slots - n_first, strip)) != LSMRC_OK) return rc;
+    return ring_enqueue_compute(h, L, n_frames, strip);
 }
 
 int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void* h_first, int n_first, const void* h_second)

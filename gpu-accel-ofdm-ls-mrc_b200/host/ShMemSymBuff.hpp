@@ -152,6 +152,10 @@ class ShMemSymBuff {
         }
         return slot(w);
     }
+    // Producers that keep several slots in flight (ring_feeder's PipelinedWriter) address slots directly and check
+    // the read index themselves; slots are still published one by one, in order, with commitWriteSlot().
+    complexF* slotAt(int i) { return slot(i); }
+    int readIndex() const { return load(kRead); }
     void commitWriteSlot()
     {
         int w = load(kWrite);

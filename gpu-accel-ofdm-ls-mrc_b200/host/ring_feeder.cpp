@@ -5,10 +5,12 @@
 // Creates the segment (master), waits for a consumer, streams the frames of a file.
 //
 //   ring_feeder --file rx.bin --rows A --cols N --prefix C --syms S --ring L [--frames F]
-//               [--shm /blah] [--repeat R] [--nowait] [--threads T] [--stream-stores]
+//               [--shm /blah] [--repeat R] [--nowait] [--threads T] [--stream-stores] [--first-lap-only]
 // Slots are filled with non-temporal stores when --threads T > 1 or --stream-stores is given (see stream_copy).
-// --threads T > 1 copies every symbol into its slot with T helper threads (a radio front end delivers
-// the antennas in parallel; one memcpy thread tops out near 9 GB/s and would hide what the consumer can do).
+// --threads T > 1 keeps T slots in flight, one producer thread each, published in order (PipelinedWriter; a radio
+// front end delivers in parallel; one memcpy thread tops out near 9 GB/s and would hide what the consumer can do).
+// --first-lap-only (with --threads) writes every slot once and afterwards only publishes it again: the consumer's
+// ceiling without any producer traffic in host memory (diagnostic).
 // rx.bin holds [F][S][A][N+C] complex64.  --nowait uses writeNextSymbolNoWait like the
 // reference producer (can overrun a slow reader); the default blocks on a full ring.
 #include <cstdio>
@@ -52,67 +54,80 @@ static void stream_copy(void* dst, const void* src, size_t bytes)
 #endif
 }
 
-// Splits one symbol copy over a few persistent helper threads (spin-synchronised: copies are ~100 us apart).
-class ParallelCopy {
+// Several producer threads, one whole slot each: thread i takes the next unwritten symbol, waits until its slot has been
+// released by the reader, fills it, and flags it; the main thread publishes slots strictly in order.  (Round 2 first
+// split every symbol over the threads with a join per symbol -- a 45 us copy paid ~10 us of fork/join; whole slots in
+// flight need no join at all, as the antennas of a radio front end arrive in parallel anyway.)
+class PipelinedWriter {
    public:
-    explicit ParallelCopy(int n) : n_(n > 1 ? n : 1)
+    PipelinedWriter(ShMemSymBuff& ring, int threads, bool copy_every_lap)
+        : ring_(ring), n_(threads > 1 ? threads : 1), len_(ring.slots()), every_lap_(copy_every_lap), done_((size_t)ring.slots())
     {
-        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+        for (auto& d : done_) d.store(0, std::memory_order_relaxed);
     }
-    ~ParallelCopy()
+    // symbol j comes from src(j); returns false when the reader went away
+    template <class Src>
+    bool run(long long total, Src&& src)
     {
-        stop_.store(true, std::memory_order_release);
-        gen_.fetch_add(1, std::memory_order_release);
-        for (auto& t : workers_) t.join();
-    }
-    void copy(void* dst, const void* src, size_t bytes)
-    {
-        if (n_ == 1) {
-            stream_copy(dst, src, bytes);
-            return;
+        std::vector<std::thread> workers;
+        for (int i = 0; i < n_; ++i)
+            workers.emplace_back([this, total, &src] {
+                for (;;) {
+                    const long long j = next_.fetch_add(1, std::memory_order_relaxed);
+                    if (j >= total) return;
+                    if (!wait_free(j)) return;
+                    if (every_lap_ || j < len_) stream_copy(ring_.slotAt((int)(j % len_)), src(j), ring_.slotBytes());
+                    done_[(size_t)(j % len_)].store(j + 1, std::memory_order_release);
+                }
+            });
+        bool ok = true;
+        for (long long j = 0; j < total && ok; ++j) {
+            while (done_[(size_t)(j % len_)].load(std::memory_order_acquire) != j + 1) {
+                if (ring_.readerGone()) {
+                    ok = false;
+                    break;
+                }
+                sched_yield();
+            }
+            if (ok) {
+                ring_.commitWriteSlot();
+                committed_.store(j + 1, std::memory_order_release);
+            }
         }
-        dst_ = static_cast<char*>(dst);
-        src_ = static_cast<const char*>(src);
-        bytes_ = bytes;
-        done_.store(0, std::memory_order_relaxed);
-        gen_.fetch_add(1, std::memory_order_release);
-        part(0);
-        while (done_.load(std::memory_order_acquire) != n_ - 1) sched_yield();
+        if (!ok) {
+            abort_.store(true, std::memory_order_release);
+            next_.store(total, std::memory_order_relaxed);
+        }
+        for (auto& t : workers) t.join();
+        return ok;
     }
 
    private:
-    void part(int i)
+    // slot j % len is free once the reader has released symbol j - len; one slot of the ring always stays empty
+    bool wait_free(long long j)
     {
-        const size_t chunk = ((bytes_ + n_ - 1) / n_ + 63) & ~(size_t)63;
-        const size_t b = chunk * (size_t)i, e = b + chunk < bytes_ ? b + chunk : bytes_;
-        if (b < e) stream_copy(dst_ + b, src_ + b, e - b);
-    }
-    void loop(int i)
-    {
-        unsigned seen = 0;
         for (;;) {
-            unsigned g;
-            while ((g = gen_.load(std::memory_order_acquire)) == seen) sched_yield();
-            seen = g;
-            if (stop_.load(std::memory_order_acquire)) return;
-            part(i);
-            done_.fetch_add(1, std::memory_order_release);
+            const long long c = committed_.load(std::memory_order_acquire);
+            const int r = ring_.readIndex();
+            const long long in_ring = ((c % len_) - r + len_) % len_;  // == available(); read after c, so never too small
+            if (j - (c - in_ring) <= len_ - 2) return true;
+            if (abort_.load(std::memory_order_acquire) || ring_.readerGone()) return false;
+            sched_yield();
         }
     }
+    ShMemSymBuff& ring_;
     int n_;
-    std::vector<std::thread> workers_;
-    std::atomic<unsigned> gen_{0};
-    std::atomic<int> done_{0};
-    std::atomic<bool> stop_{false};
-    char* dst_ = nullptr;
-    const char* src_ = nullptr;
-    size_t bytes_ = 0;
+    long long len_;
+    bool every_lap_;
+    std::vector<std::atomic<long long>> done_;
+    std::atomic<long long> next_{0}, committed_{0};
+    std::atomic<bool> abort_{false};
 };
 
 int main(int argc, char** argv)
 {
     int rows = numOfRows, cols = dimension, cp = prefix, syms = lenOfBuffer, ring = 0, frames = -1, repeat = 1, threads = 1;
-    bool nowait = false, stream_stores = false;
+    bool nowait = false, stream_stores = false, first_lap_only = false;
     std::string shm = shmemID, file;
     for (int i = 1; i < argc; ++i) {
         auto val = [&](const char* name) -> const char* {
@@ -132,6 +147,7 @@ int main(int argc, char** argv)
         else if ((v = val("--file"))) file = v;
         else if (std::strcmp(argv[i], "--nowait") == 0) nowait = true;
         else if (std::strcmp(argv[i], "--stream-stores") == 0) stream_stores = true;
+        else if (std::strcmp(argv[i], "--first-lap-only") == 0) first_lap_only = true;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
@@ -153,23 +169,28 @@ int main(int argc, char** argv)
     in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(buf.size() * sizeof(complexF)));
 
     ShMemSymBuff ringbuf(shm, /*isMaster=*/1, rows, cols, cp, ring);
-    ParallelCopy pc(threads);
-    for (int r = 0; r < repeat; ++r)
-        for (int f = 0; f < frames; ++f)
-            for (int s = 0; s < syms; ++s) {
-                complexF* sym = buf.data() + ((size_t)f * syms + (size_t)s) * slot;
-                if (threads > 1 || stream_stores) {
-                    // same protocol as writeNextSymbolWithWait, with the slot filled by the helper threads
-                    complexF* dst = ringbuf.acquireWriteSlot();
-                    if (!dst) break;  // reader gone
-                    pc.copy(dst, sym, ringbuf.slotBytes());
-                    ringbuf.commitWriteSlot();
-                } else if (nowait) {
-                    ringbuf.writeNextSymbolNoWait(sym);
-                } else {
-                    ringbuf.writeNextSymbolWithWait(sym);
+    if (threads > 1) {
+        const long long per_lap = (long long)frames * syms;
+        PipelinedWriter pw(ringbuf, threads, !first_lap_only);
+        pw.run(per_lap * repeat, [&](long long j) { return buf.data() + (size_t)(j % per_lap) * slot; });
+    } else {
+        for (int r = 0; r < repeat; ++r)
+            for (int f = 0; f < frames; ++f)
+                for (int s = 0; s < syms; ++s) {
+                    complexF* sym = buf.data() + ((size_t)f * syms + (size_t)s) * slot;
+                    if (stream_stores) {
+                        // same protocol as writeNextSymbolWithWait, with the slot filled by non-temporal stores
+                        complexF* dst = ringbuf.acquireWriteSlot();
+                        if (!dst) break;  // reader gone
+                        stream_copy(dst, sym, ringbuf.slotBytes());
+                        ringbuf.commitWriteSlot();
+                    } else if (nowait) {
+                        ringbuf.writeNextSymbolNoWait(sym);
+                    } else {
+                        ringbuf.writeNextSymbolWithWait(sym);
+                    }
                 }
-            }
+    }
     // keep the segment alive until the reader has drained it and gone away
     while (ringbuf.available() > 0 && !ringbuf.readerGone()) sched_yield();
     return 0;

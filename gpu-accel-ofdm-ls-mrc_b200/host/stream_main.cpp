@@ -117,6 +117,11 @@ static void run_stream(const Args& a, int gpu, const std::string& shm, const std
             }
         }
     };
+    if (lsmrc_ring_prepare(ls.handle) < 0) {  // lane buffers exist before the clock starts
+        fprintf(stderr, "ring_prepare: %s\n", lsmrc_last_error(ls.handle));
+        res->rc = 1;
+        return;
+    }
     const auto t0 = std::chrono::steady_clock::now();
     auto t_first = t0;
     // Up to n_lanes submissions (of up to `batch` frames each) are in flight.  Two things trail them, both in order:

@@ -144,6 +144,9 @@ int lsmrc_get_channel_device(lsmrc_handle h, void *d_hconj /* [A][K] */, void *d
  *      returns at once; wait() blocks until that lane is done and hands back pointers to
  *      the lane's pinned result buffers (valid until the lane is submitted again). ------ */
 int lsmrc_ring_submit_frame(lsmrc_handle h, int lane, const void *h_slots, size_t slot_stride_bytes);
+/* Allocates the lanes (streams, device staging, pinned result buffers) now instead of inside the first submission --
+ * tens of milliseconds of cudaMalloc / cudaMallocHost that a streaming consumer wants behind it before frames arrive. */
+int lsmrc_ring_prepare(lsmrc_handle h);
 /* one frame that wraps around the end of the ring: n_first slots at h_first, the other S - n_first at h_second */
 int lsmrc_ring_submit_split(lsmrc_handle h, int lane, const void *h_first, int n_first,
                             const void *h_second);

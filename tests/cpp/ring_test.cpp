@@ -2,6 +2,7 @@
 // modes:
 //   selftest <shm>            producer thread + consumer thread over one segment: layout, order,
 //                             wrap-around, flow control, whole-frame views, CP strip
+//   dump <shm> A N C L count file   consumer that writes every slot to a file
 //   read <shm> A N C L count  consumer for a foreign producer (the reference's own ring class,
 //                             see oracle/ref_ring_writer.cpp): checks `count` patterned symbols
 #include <cstdio>
@@ -96,6 +97,23 @@ static int read_foreign(const char* shm, int A, int N, int C, int L, int count)
     return 0;
 }
 
+// consumer that appends every slot it reads to a file (checks multi-threaded producers: order and content)
+static int dump_foreign(const char* shm, int A, int N, int C, int L, int count, const char* out_path)
+{
+    ShMemSymBuff slave(shm, 0, A, N, C, L);
+    FILE* out = fopen(out_path, "wb");
+    if (!out) return fail("cannot open the dump file");
+    for (int s = 0; s < count; ++s) {
+        const complexF* p = slave.peekSlot();
+        fwrite(p, sizeof(complexF), slave.slotElems(), out);
+        if (s % 7 == 3) usleep(200);  // a reader that stalls now and then: the producers must wait for free slots
+        slave.releaseSlots(1);
+    }
+    fclose(out);
+    printf("ring dump ok (%d symbols)\n", count);
+    return 0;
+}
+
 // writer end of the return ring (ShMemBitsBuff, master): frame i carries bytes (i*131 + j*7) & 255
 static int bits_write(const char* name, long frame_bytes, int slots, int frames)
 {
@@ -120,6 +138,8 @@ int main(int argc, char** argv)
     if (argc >= 3 && std::strcmp(argv[1], "selftest") == 0) return selftest(argv[2]);
     if (argc >= 8 && std::strcmp(argv[1], "read") == 0)
         return read_foreign(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
+    if (argc >= 9 && std::strcmp(argv[1], "dump") == 0)
+        return dump_foreign(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), argv[8]);
     fprintf(stderr, "usage: ring_test selftest <shm> | read <shm> A N C L count\n");
     return 2;
 }

@@ -52,6 +52,37 @@ def test_ring_reads_what_the_reference_producer_writes(ring_test_bin):
     assert f"ring read ok ({count} symbols)" in r.stdout
 
 
+@pytest.mark.parametrize("threads,ring", [(4, 9), (3, 5), (1, 6)])
+def test_feeder_with_several_producer_threads_keeps_order(ring_test_bin, tmp_path, threads, ring):
+    """host/ring_feeder --threads T (T slots in flight, published in order) -> ring -> reader: every slot arrives once, in
+    order, intact, over several laps of a ring that is shorter than a frame plus the threads in flight"""
+    import numpy as np
+    assert subprocess.run(["make", "-C", HOST, "--no-print-directory", "bin/ring_feeder"], capture_output=True).returncode == 0
+    A, N, C, S, frames, repeat = 3, 64, 16, 7, 2, 5
+    rng = np.random.default_rng(11)
+    rx = rng.standard_normal((frames, S, A, N + C, 2)).astype(np.float32)
+    rx.tofile(tmp_path / "rx.bin")
+    name = "/lsmrc_feed_" + uuid.uuid4().hex[:8]
+    count = frames * S * repeat
+    rd = subprocess.Popen([ring_test_bin, "dump", name, str(A), str(N), str(C), str(ring), str(count), str(tmp_path / "dump.bin")],
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        time.sleep(0.05)
+        fd = subprocess.run([os.path.join(HOST, "bin", "ring_feeder"), "--file", str(tmp_path / "rx.bin"), "--rows", str(A), "--cols", str(N),
+                             "--prefix", str(C), "--syms", str(S), "--ring", str(ring), "--shm", name, "--repeat", str(repeat),
+                             "--threads", str(threads)], capture_output=True, text=True, timeout=60)
+        out, err = rd.communicate(timeout=60)
+    finally:
+        if rd.poll() is None:
+            rd.kill()
+        if os.path.exists("/dev/shm" + name):
+            os.unlink("/dev/shm" + name)
+    assert fd.returncode == 0, fd.stderr
+    assert rd.returncode == 0, err
+    got = np.fromfile(tmp_path / "dump.bin", np.float32).reshape(repeat, frames, S, A, N + C, 2)
+    assert np.array_equal(got, np.broadcast_to(rx, got.shape))
+
+
 def test_host_programs_build_without_cuda_headers(ofdm):
     ofdm.load_library()  # make sure the .so the programs link exists
     r = subprocess.run(["make", "-C", HOST, "--no-print-directory"], capture_output=True, text=True)
