@@ -293,6 +293,29 @@ def scaling_c4_leg(m, dev, local, rank, world, dist, peak, frames=512, steps=5, 
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     ms_max = float(tmax[0].item())
     per_gpu_gbs = frames * steps * cfg.algorithmic_bytes_per_frame / (ms_max * 1e-3) / 1e9
+    gather = None
+    if dist is not None:
+        # the one optional exchange of the path: decoded bits of every rank to rank 0 over NCCL, after and
+        # outside the timed region; checked by a checksum of checksums (every rank's byte sum travels separately)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m.sharding.gather_rows(bits[:1].contiguous(), world)        # communicator warm-up
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        g0.record(stream)
+        everything = m.sharding.gather_rows(bits, frames * world)
+        g1.record(stream)
+        torch.cuda.synchronize(dev)
+        sums = torch.zeros(world, device=dev, dtype=torch.int64)
+        sums[rank] = bits.sum(dtype=torch.int64)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        ok = None
+        if rank == 0:
+            got = everything.view(world, -1).sum(dim=1, dtype=torch.int64)
+            ok = bool(torch.equal(got, sums)) and bool(torch.equal(everything[:frames], bits))
+        gather = {"backend": dist.get_backend(), "to_rank": 0, "bytes_per_gpu": int(bits.numel()), "ms": g0.elapsed_time(g1),
+                  "share_of_step": g0.elapsed_time(g1) / (ms_max / steps), "checksums_match": ok,
+                  "what": "sharding.gather_rows of the packed bits of all ranks, after the timed region"}
+        del everything
     del rx, rx_f, comb, bits, want
     torch.cuda.empty_cache()
     return {"workload": "c4: 4096-pt FFT, CP 288, 256 antennas, 1 pilot + 13 data symbols, 64-QAM", "scaling": "weak",
@@ -302,7 +325,7 @@ def scaling_c4_leg(m, dev, local, rank, world, dist, peak, frames=512, steps=5, 
             "algorithmic_gbs_per_gpu": per_gpu_gbs, "frac_of_hbm_peak": per_gpu_gbs / peak,
             "pilot_kernel_ms": statistics.mean(p_ms), "data_kernel_ms": statistics.mean(d_ms),
             "differing_bit_bytes_vs_source_all_ranks": int(t[1].item()) if dist is not None else errs,
-            "frames_checked_per_gpu": frames, "plan": plan}
+            "frames_checked_per_gpu": frames, "plan": plan, "bits_gather": gather}
 
 
 def cpu_baseline(cfg, n_threads, budget_s=12.0):
@@ -699,6 +722,38 @@ def main():
                "h2d_gbs": world * h2d * n_e2e / dt / 1e9, "host_input_bytes_per_step": int(h_rx.nbytes),
                "h2d_copy": "strided, cyclic prefix left on the host" if strip else "whole slots",
                "bit_mismatch_vs_device_path": e2e_err}
+        if not args.no_extras:
+            # The same frames as the radio puts them on the wire (int16 I/Q; rx_and_corr.cpp:283 has UHD convert them to
+            # complex float on the host), converted on the device after the copy: half the PCIe bytes.  A secondary figure --
+            # `e2e` above stays the complex-float call the reference's interface has.
+            peak_amp = float(np.abs(h_rx.view(np.float32)).max())
+            h_iq = rcv.pinned_array(h_rx.shape + (2,), np.int16)
+            np.rint(h_rx.view(np.float32).reshape(h_iq.shape) * (8191.0 / peak_amp), out=h_rx.view(np.float32).reshape(h_iq.shape))
+            h_iq[...] = h_rx.view(np.float32).reshape(h_iq.shape)      # (h_rx is scratch from here on)
+            sc = 1.0 / 32767.0
+            h_bits16 = np.empty_like(h_bits)
+            for _ in range(3):
+                rcv.demod_frames_host_sc16(h_iq, Fe, sc, h_comb, h_bits)
+            h_bits16[...] = h_bits
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                rcv.demod_frames_host_sc16(h_iq, Fe, sc, h_comb, h_bits)
+            dt16 = time.perf_counter() - t0
+            t = torch.tensor([dt16], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt16 = float(t.item())
+            # check: the complex-float call on the floats the host conversion gives must decode the same bits
+            h_rx.view(np.float32).reshape(h_iq.shape)[...] = h_iq.astype(np.float32) * np.float32(sc)
+            rcv.demod_frames_host(h_rx, Fe, h_comb, h_bits)
+            h2d16 = h2d // 2
+            e2e["wire_format_sc16"] = {
+                "value": world * Fe * n_e2e * cfg.antenna_samples_per_frame / dt16, "unit": UNIT, "ms_per_step": 1e3 * dt16 / n_e2e,
+                "h2d_bytes_per_step": h2d16, "h2d_gbs": world * h2d16 * n_e2e / dt16 / 1e9,
+                "api": "lsmrc_demod_frames_host_sc16 (int16 I/Q in pinned host memory, converted on the device)",
+                "bit_mismatch_vs_complex_float_call_on_converted_samples": int(np.unpackbits(h_bits16 ^ h_bits).sum()),
+                "note": "not the reference's interface (complex float): what the link carries when the radio's wire format is kept"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

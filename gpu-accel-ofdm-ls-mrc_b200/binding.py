@@ -32,6 +32,8 @@ ABI = {
     "lsmrc_demod_frames_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsmrc_demod_frames_device_soft": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float]),
     "lsmrc_demod_frames_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsmrc_demod_frames_host_sc16": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsmrc_sc16_to_fc32_device": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_float, c_void_p]),
     "lsmrc_first_vector": (c_int, [c_void_p, c_void_p, c_int]),
     "lsmrc_demod_one_symbol": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "lsmrc_get_channel": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -214,6 +216,14 @@ class LsMrcReceiver:
     def demod_frames_host(self, h_rx, n_frames, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
         self._ck(self.lib.lsmrc_demod_frames_host(self.h, _ptr(h_rx), n_frames, _ptr(h_hconj), _ptr(h_hsqrd),
                                                   _ptr(h_combined), _ptr(h_bits)))
+
+    def demod_frames_host_sc16(self, h_rx_iq, n_frames, scale, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
+        """frames in the radio's wire format: h_rx_iq [F,S,A,N+C,2] int16, sample = int16 * scale (converted on the device)"""
+        self._ck(self.lib.lsmrc_demod_frames_host_sc16(self.h, _ptr(h_rx_iq), n_frames, float(scale), _ptr(h_hconj), _ptr(h_hsqrd),
+                                                       _ptr(h_combined), _ptr(h_bits)))
+
+    def sc16_to_fc32_device(self, d_iq, rows, row_len_in, skip, row_len_out, scale, d_out):
+        self._ck(self.lib.lsmrc_sc16_to_fc32_device(self.h, _ptr(d_iq), rows, row_len_in, skip, row_len_out, float(scale), _ptr(d_out)))
 
     def demod_numpy(self, rx: np.ndarray, want_channel=True):
         """Convenience for tests: rx [F,S,A,N+C] complex64 host array -> dict of host arrays."""

@@ -448,6 +448,7 @@ struct Lane {
     cudaEvent_t copied = nullptr, done = nullptr;
     cudaEvent_t t_start = nullptr, t_kernels = nullptr;  // timeline of the ring path (lsmrc_ring_trace): submission enqueued, kernels finished
     float2* d_rx = nullptr;     // [max_frames][S][A][N+C]
+    short2* d_rx16 = nullptr;   // the same frames in the radio's wire format (int16 I/Q), allocated by the first sc16 call
     float2* d_hconj = nullptr;  // [max_frames][A][K] (reference layout, only when the caller wants it back)
     float2* d_comb = nullptr;   // [max_frames][S-1][K]
     uint8_t* d_bits = nullptr;  // [max_frames][S-1][row]
@@ -831,6 +832,7 @@ void free_lane(Lane& L)
 {
     if (L.st) cudaStreamSynchronize(L.st);
     cudaFree(L.d_rx);
+    cudaFree(L.d_rx16);
     cudaFree(L.d_hconj);
     free_chan(L.ch);
     cudaFree(L.d_comb);
@@ -1255,8 +1257,26 @@ int lsmrc_zf_apply(lsmrc_handle h, const void* d_hzf, const void* d_xd, int n_an
     return LSMRC_OK;
 }
 
-int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,
-                            void* h_combined, void* h_bits)
+// wire-format samples to complex float: out[r][n] = float(in[r][skip + n]) * scale (k_sc16_to_fc32)
+static int launch_sc16_to_fc32(lsmrc_ctx* h, cudaStream_t st, float2* out, const short2* in, long long rows, int n_in, int skip, int n_out,
+                               float scale)
+{
+    const bool vec2 = ((n_in | skip | n_out) & 1) == 0 && reinterpret_cast<uintptr_t>(in) % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    long long blocks = (rows * (n_out / (vec2 ? 2 : 1)) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    if (vec2)
+        k_sc16_to_fc32<true><<<(unsigned)blocks, 256, 0, st>>>(out, in, rows, n_in, skip, n_out, scale);
+    else
+        k_sc16_to_fc32<false><<<(unsigned)blocks, 256, 0, st>>>(out, in, rows, n_in, skip, n_out, scale);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return LSMRC_OK;
+}
+
+// sc16: h_rx holds the radio's wire format (int16 I/Q, 4 bytes per sample), converted on the device after the copy
+static int demod_frames_host_impl(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd, void* h_combined,
+                                  void* h_bits, bool sc16, float scale)
 {
     if (!h || !h_rx || !h_combined) return fail(h, LSMRC_ERR_INVALID, "null argument");
     if (n_frames < 0) return fail(h, LSMRC_ERR_INVALID, "n_frames < 0");
@@ -1265,12 +1285,13 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     CK(h, cudaSetDevice(h->cfg.device));
     const lsmrc_config& c = h->cfg;
     const size_t nd = (size_t)(c.n_sym - 1);
-    const size_t rx_fb = h->frame_elems * sizeof(float2);
+    const size_t elem = sc16 ? sizeof(short2) : sizeof(float2);  // bytes per sample on the host
+    const size_t rx_fb = h->frame_elems * elem;
     // Latency path: a batch the one-launch kernel takes, in pinned host memory and small enough that
     // PCIe latency rather than bandwidth decides, is processed in place -- the kernel loads the
     // antenna-samples from and stores the results to the host buffers directly, so the call is one
     // launch and one sync instead of a copy in, the kernels, and up to four copies out.
-    if (h->oneshot && h->zero_copy && h->one_ops && nd > 0 && rx_fb * (size_t)n_frames <= kZeroCopyBytes &&
+    if (!sc16 && h->oneshot && h->zero_copy && h->one_ops && nd > 0 && rx_fb * (size_t)n_frames <= kZeroCopyBytes &&
         h->one_ops->split(n_frames, c.n_sym - 1, c.n_ant, h->n_sms, h->smem_optin) > 0) {
         void* a_rx = mapped_alias(h_rx);
         void* a_cb = mapped_alias(h_combined);
@@ -1305,7 +1326,10 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     pin_bt.pin(h_bits, bt_fb * n_frames);
 
     // strided H2D that skips the cyclic prefix: worth it when rows are long enough for the copy engine
-    const bool strip_cp = strip_cp_on_h2d(h);
+    const bool strip_cp = sc16 ? (h->h2d_strip_cp && c.cp_len > 0 && (size_t)c.fft_size * elem >= h->h2d_strip_min_row) : strip_cp_on_h2d(h);
+    if (sc16)
+        for (Lane& L : h->lanes)
+            if (!L.d_rx16) CK(h, cudaMalloc(&L.d_rx16, (size_t)c.max_frames * h->frame_elems * sizeof(short2)));
     int chunk_idx = 0;
     for (int f0 = 0; f0 < n_frames; f0 += c.max_frames, ++chunk_idx) {
         const int nf = (n_frames - f0 < c.max_frames) ? (n_frames - f0) : c.max_frames;
@@ -1313,16 +1337,23 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
         const char* src = static_cast<const char*>(h_rx) + (size_t)f0 * rx_fb;
         RxLayout dense_lay{};
         dense_lay.dense = true;
+        void* d_in = sc16 ? static_cast<void*>(L.d_rx16) : static_cast<void*>(L.d_rx);
+        const long long n_rows = (long long)nf * c.n_sym * c.n_ant;
         if (strip_cp) {
             // the cyclic prefix is never used: leave it on the host (C/(N+C) of the PCIe bytes)
-            const size_t row = (size_t)c.fft_size * sizeof(float2), pitch = (size_t)(c.fft_size + c.cp_len) * sizeof(float2);
-            CK(h, cudaMemcpy2DAsync(L.d_rx, row, src + (size_t)c.cp_len * sizeof(float2), pitch, row,
-                                    (size_t)nf * c.n_sym * c.n_ant, cudaMemcpyHostToDevice, L.st));
+            const size_t row = (size_t)c.fft_size * elem, pitch = (size_t)(c.fft_size + c.cp_len) * elem;
+            CK(h, cudaMemcpy2DAsync(d_in, row, src + (size_t)c.cp_len * elem, pitch, row, (size_t)n_rows, cudaMemcpyHostToDevice, L.st));
         } else {
-            CK(h, cudaMemcpyAsync(L.d_rx, src, rx_fb * nf, cudaMemcpyHostToDevice, L.st));
+            CK(h, cudaMemcpyAsync(d_in, src, rx_fb * nf, cudaMemcpyHostToDevice, L.st));
+        }
+        if (sc16) {
+            // wire format -> complex float on the device, always into dense rows (what is left of the prefix goes here)
+            rc = launch_sc16_to_fc32(h, L.st, L.d_rx, L.d_rx16, n_rows, strip_cp ? c.fft_size : c.fft_size + c.cp_len,
+                                     strip_cp ? 0 : c.cp_len, c.fft_size, scale);
+            if (rc != LSMRC_OK) return rc;
         }
         rc = launch_frames(h, L.st, L.d_rx, nf, L.ch, h_hconj ? L.d_hconj : nullptr, nullptr, L.d_comb,
-                           h_bits ? L.d_bits : nullptr, false, strip_cp ? &dense_lay : nullptr);
+                           h_bits ? L.d_bits : nullptr, false, (strip_cp || sc16) ? &dense_lay : nullptr);
         if (rc != LSMRC_OK) return rc;
         if (nd > 0)
             CK(h, cudaMemcpyAsync(static_cast<char*>(h_combined) + (size_t)f0 * cb_fb, L.d_comb, cb_fb * nf,
@@ -1339,6 +1370,29 @@ int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void
     }
     for (Lane& L : h->lanes) CK(h, cudaStreamSynchronize(L.st));
     return LSMRC_OK;
+}
+
+int lsmrc_demod_frames_host(lsmrc_handle h, const void* h_rx, int n_frames, void* h_hconj, void* h_hsqrd,
+                            void* h_combined, void* h_bits)
+{
+    return demod_frames_host_impl(h, h_rx, n_frames, h_hconj, h_hsqrd, h_combined, h_bits, false, 1.f);
+}
+
+int lsmrc_demod_frames_host_sc16(lsmrc_handle h, const int16_t* h_rx_iq, int n_frames, float scale, void* h_hconj, void* h_hsqrd,
+                                 void* h_combined, void* h_bits)
+{
+    return demod_frames_host_impl(h, h_rx_iq, n_frames, h_hconj, h_hsqrd, h_combined, h_bits, true, scale);
+}
+
+int lsmrc_sc16_to_fc32_device(lsmrc_handle h, const int16_t* d_iq, long long rows, int row_len_in, int skip, int row_len_out, float scale,
+                              void* d_out)
+{
+    if (!h || !d_iq || !d_out) return fail(h, LSMRC_ERR_INVALID, "null argument");
+    if (rows < 0 || row_len_out < 0 || skip < 0 || (long long)skip + row_len_out > row_len_in) return fail(h, LSMRC_ERR_INVALID, "bad row geometry");
+    if (rows == 0 || row_len_out == 0) return LSMRC_OK;
+    CK(h, cudaSetDevice(h->cfg.device));
+    return launch_sc16_to_fc32(h, compute_stream(h), static_cast<float2*>(d_out), reinterpret_cast<const short2*>(d_iq), rows, row_len_in, skip,
+                               row_len_out, scale);
 }
 
 int lsmrc_first_vector(lsmrc_handle h, const void* rx_sym, int on_device)

@@ -1788,6 +1788,36 @@ __global__ void k_drop_prefix(float2* __restrict__ out, const float2* __restrict
     }
 }
 
+// Receive front end, sample format.  The radio's wire format is interleaved int16 I/Q: rx_and_corr.cpp:283 asks UHD for cpu
+// format "fc32" over wire format "sc16", i.e. UHD converts on the host (fc32 = sc16 * scale, scale = 1/32767 by default) and
+// the reference ships 8 bytes per sample to the GPU.  Here the wire format crosses PCIe (half the bytes) and is converted on
+// the device, dropping `skip` leading samples of every row (the cyclic prefix) on the way:
+// out[r][n] = float(in[r][skip + n]) * scale -- int16 -> float is exact and the product is one rounding, so the result is
+// bit-identical to the host conversion.  VEC2: two samples per thread (n_in, skip, n_out even; 8-byte loads, 16-byte stores).
+template <bool VEC2>
+__global__ void k_sc16_to_fc32(float2* __restrict__ out, const short2* __restrict__ in, long long rows, int n_in, int skip, int n_out,
+                               float scale)
+{
+    constexpr int V = VEC2 ? 2 : 1;
+    const int per_row = n_out / V;
+    const long long total = rows * per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per_row;
+        const int c = (int)(i - r * per_row) * V;
+        if constexpr (VEC2) {
+            const int2 w = *reinterpret_cast<const int2*>(in + r * n_in + skip + c);
+            const short2 a = *reinterpret_cast<const short2*>(&w.x), b = *reinterpret_cast<const short2*>(&w.y);
+            float4 o;
+            o.x = __int2float_rn(a.x) * scale, o.y = __int2float_rn(a.y) * scale;
+            o.z = __int2float_rn(b.x) * scale, o.w = __int2float_rn(b.y) * scale;
+            *reinterpret_cast<float4*>(out + r * n_out + c) = o;
+        } else {
+            const short2 a = in[r * n_in + skip + c];
+            out[r * n_out + c] = make_float2(__int2float_rn(a.x) * scale, __int2float_rn(a.y) * scale);
+        }
+    }
+}
+
 // gpuLS.cu:158-182 findHs: hconj[a][k] = conj(yfft[a][k+1] / x[k])   (x: K entries, bin order)
 __global__ void k_find_hs(const float2* __restrict__ yfft, float2* __restrict__ hconj, const float2* __restrict__ x,
                           int rows, int n, int x_row_stride)

@@ -125,6 +125,21 @@ int lsmrc_llr_from_combined(lsmrc_handle h, const void *d_combined, const void *
 int lsmrc_demod_frames_host(lsmrc_handle h, const void *h_rx, int n_frames, void *h_hconj,
                             void *h_hsqrd, void *h_combined, void *h_bits);
 
+/* ---- wire-format ingest (the producer side; not in the reference).  The reference's receive program asks
+ *      UHD for cpu format "fc32" over wire format "sc16" (rx_and_corr.cpp:283): the radio's int16 I/Q samples are converted
+ *      to complex float ON THE HOST (fc32 = sc16 * scale; UHD's default full scale gives scale = 1/32767) and every sample
+ *      then crosses PCIe as 8 bytes.  Host-fed operation is PCIe-bound, so these calls take the wire format itself --
+ *      h_rx_iq [F][S][A][N+C][2] int16, 4 bytes per sample -- and convert on the device after the copy: half the bytes on
+ *      the link.  int16 -> float is exact and the product rounds once, so the receiver sees bit-for-bit the floats the host
+ *      conversion would have produced; everything else is lsmrc_demod_frames_host. */
+int lsmrc_demod_frames_host_sc16(lsmrc_handle h, const int16_t *h_rx_iq, int n_frames, float scale, void *h_hconj,
+                                 void *h_hsqrd, void *h_combined, void *h_bits);
+/* The conversion alone, device to device: out[r][n] = (float)in[r][skip + n] * scale for `rows` rows of row_len_in int16
+ * I/Q pairs, keeping row_len_out samples from position `skip` (e.g. skip = C, row_len_out = N drops the cyclic prefix);
+ * d_out is complex64 [rows][row_len_out]. */
+int lsmrc_sc16_to_fc32_device(lsmrc_handle h, const int16_t *d_iq, long long rows, int row_len_in, int skip, int row_len_out,
+                              float scale, void *d_out);
+
 /* ---- per-symbol entry points (replace gpuLS::firstVector gpuLS.cu:351 and
  *      gpuLS::demodOneSymbol :410).  rx_sym is one ring slot [A][N+C]; on_device says
  *      where it lives.  The channel estimate stays inside the handle between calls. ---- */

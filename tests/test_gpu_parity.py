@@ -187,6 +187,69 @@ def test_small_pinned_frames_are_processed_in_place(ofdm, oracle, dims, how):
     assert_close(out2["combined"], got["comb"], "staged vs in place", tol=2e-6)
 
 
+def _to_wire_format(rx):
+    """what the radio would have sent for these frames: int16 I/Q at 12 dB below full scale (clipped), and the complex
+    float samples UHD's host-side converter makes of them (fc32 = sc16 * 1/32767, rx_and_corr.cpp:283)"""
+    scale = np.float32(1.0 / 32767.0)
+    peak = np.abs(rx.view(np.float32)).max()
+    iq = np.clip(np.rint(rx.view(np.float32).reshape(rx.shape + (2,)) * (8191.0 / peak)), -32768, 32767).astype(np.int16)
+    as_float = (iq.astype(np.float32) * scale).reshape(rx.shape + (2,)).view(np.complex64)[..., 0]
+    return iq, scale, np.ascontiguousarray(as_float)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(4, 64, 16, 16, 2, 5), (8, 256, 32, 5, 6, 3), (16, 1024, 64, 6, 4, 7), (6, 1024, 9, 3, 6, 2),
+                                  (8, 2048, 144, 4, 4, 3), (5, 4096, 288, 3, 6, 2)])
+def test_wire_format_ingest_equals_host_conversion(ofdm, oracle, dims):
+    """lsmrc_demod_frames_host_sc16: int16 I/Q over the link, converted on the device.  The oracle runs on the floats UHD's
+    host conversion gives for the same int16 samples (1e-5 / bits exact); and because int16 -> float * scale is exact
+    up to one rounding, the complex-float entry point fed with those floats must agree BIT FOR BIT."""
+    A, N, C, S, b, F = dims
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=SNR[b], seed=31)
+    iq, scale, rx_f = _to_wire_format(d["rx"])
+    ref = oracle.demod_frames(rx_f, d["pilot_asc"], b, C)
+    K = N - 1
+    with ofdm.LsMrcReceiver(A, N, C, S, b, max_frames=2) as r:       # several chunks over the lanes
+        r.set_pilot(d["pilot_asc"])
+        r.set_oneshot(0)
+        comb = np.empty((F, S - 1, K), np.complex64)
+        bits = np.empty((F, S - 1, (K * b + 7) // 8), np.uint8)
+        hc = np.empty((F, A, K), np.complex64)
+        hs = np.empty((F, K), np.float32)
+        r.demod_frames_host_sc16(iq, F, scale, comb, bits, hc, hs)
+        same = r.demod_numpy(rx_f)
+    assert_close(hc, ref["hconj"], "Hconj")
+    assert_close(hs, ref["hsqrd"], "sum|H|^2")
+    assert_close(comb, ref["combined"], "combined")
+    assert_bits_match(bits, ref["bits"], ref["combined"], b, f"{dims} sc16", got_combined=comb)
+    assert np.array_equal(comb.view(np.uint32), same["combined"].view(np.uint32))
+    assert np.array_equal(hc.view(np.uint32), same["hconj"].view(np.uint32))
+    assert np.array_equal(bits, same["bits"])
+
+
+@pytest.mark.gpu
+def test_wire_format_conversion_alone(ofdm):
+    """lsmrc_sc16_to_fc32_device against numpy for even and odd row geometries (vector and scalar kernels)"""
+    import torch
+
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    with ofdm.LsMrcReceiver(4, 64, 16, 4, 2) as r:
+        for rows, n_in, skip, n_out in [(7, 80, 16, 64), (5, 73, 9, 64), (3, 1088, 64, 1024), (2, 65, 0, 65), (4, 80, 0, 0)]:
+            iq = rng.integers(-32768, 32768, size=(rows, n_in, 2), dtype=np.int16)
+            scale = np.float32(1.0 / 32767.0)
+            d_in = torch.from_numpy(iq).to(dev)
+            d_out = torch.full((rows, max(n_out, 1), 2), -7.0, device=dev)
+            r.sc16_to_fc32_device(d_in, rows, n_in, skip, n_out, scale, d_out)
+            r.sync()
+            got = d_out.cpu().numpy()
+            if n_out == 0:
+                assert (got == -7.0).all()       # nothing to convert, nothing written
+                continue
+            want = iq[:, skip:skip + n_out].astype(np.float32) * scale
+            assert np.array_equal(got, want), (rows, n_in, skip, n_out)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims", [(16, 1024, 64, 9, 4, 40), (4, 64, 16, 16, 2, 300), (8, 2048, 144, 4, 6, 12)])
 def test_results_are_bit_repeatable(ofdm, dims):
