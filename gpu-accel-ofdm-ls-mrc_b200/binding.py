@@ -40,6 +40,8 @@ ABI = {
     "lsmrc_get_channel_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "lsmrc_ring_submit_frame": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "lsmrc_ring_prepare": (c_int, [c_void_p]),
+    "lsmrc_set_one_launch_frames": (c_int, [c_void_p, c_int]),
+    "lsmrc_one_launch_frames_count": (c_longlong, [c_void_p]),
     "lsmrc_ring_submit_split": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "lsmrc_ring_wait": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "lsmrc_ring_copy_done": (c_int, [c_void_p, c_int]),
@@ -216,6 +218,12 @@ class LsMrcReceiver:
     def demod_frames_host(self, h_rx, n_frames, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
         self._ck(self.lib.lsmrc_demod_frames_host(self.h, _ptr(h_rx), n_frames, _ptr(h_hconj), _ptr(h_hsqrd),
                                                   _ptr(h_combined), _ptr(h_bits)))
+
+    def set_one_launch_frames(self, enabled: bool):
+        self._ck(self.lib.lsmrc_set_one_launch_frames(self.h, int(enabled)))
+
+    def one_launch_frames_count(self) -> int:
+        return int(self.lib.lsmrc_one_launch_frames_count(self.h))
 
     def demod_frames_host_sc16(self, h_rx_iq, n_frames, scale, h_combined, h_bits=None, h_hconj=None, h_hsqrd=None):
         """frames in the radio's wire format: h_rx_iq [F,S,A,N+C,2] int16, sample = int16 * scale (converted on the device)"""

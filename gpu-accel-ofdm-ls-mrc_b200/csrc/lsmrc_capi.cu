@@ -34,6 +34,8 @@ struct PlanOps {
     void (*fill_twiddles)(float2*);
     cudaError_t (*prepare)(int* data_ctas_per_sm, int* pilot_ctas_per_sm);
     cudaError_t (*launch)(int mode, const KernelParams&, cudaStream_t, int max_data_ctas, unsigned* grid_out, long long* items_out);
+    // shuffle-stage plans: pilot and data items of whole frames in ONE persistent launch (lsmrc_frames_sh); nullptr otherwise
+    cudaError_t (*launch_fused)(const KernelParams&, cudaStream_t, int max_data_ctas);
 };
 
 // The one-launch kernel (MODE_ONESHOT) of a plan.  Small FFT sizes have a dedicated latency plan:
@@ -229,8 +231,29 @@ cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
         if (e != cudaSuccess) return e;
         e = occupancy_with_tmem(pilot_ctas_per_sm, lsmrc_pilot_sh<PL, MINB>, PL::THREADS, pilot_sh_smem<PL>(), 128);
         if (e != cudaSuccess) return e;
+        // ... and both in one launch (whole frames, batches large enough for one team per (frame, symbol) pair)
+        e = cudaFuncSetAttribute(lsmrc_frames_sh<PL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)data_sh_smem<PL>());
+        if (e != cudaSuccess) return e;
+        e = occupancy_with_tmem(&sh, lsmrc_frames_sh<PL, MINB>, PL::THREADS, data_sh_smem<PL>(), 128);
+        if (e != cudaSuccess) return e;
+        if (sh < *data_ctas_per_sm) *data_ctas_per_sm = sh;
     }
     return cudaSuccess;
+}
+
+// pilot + data items of whole frames on one ticket counter (shuffle-stage plans)
+template <class PL, int MINB>
+cudaError_t launch_fused_impl(const KernelParams& p, cudaStream_t st, int max_data_ctas)
+{
+    if constexpr (PL::SH > 1) {
+        const long long items = (long long)p.n_frames * p.n_groups + ((long long)p.n_frames * p.n_sym_work + PL::TEAMS - 1) / PL::TEAMS;
+        const unsigned grid = (unsigned)(items < max_data_ctas ? items : max_data_ctas);
+        lsmrc_frames_sh<PL, MINB><<<grid, PL::THREADS, data_sh_smem<PL>(), st>>>(p);
+        return cudaGetLastError();
+    } else {
+        (void)p, (void)st, (void)max_data_ctas;
+        return cudaErrorNotSupported;
+    }
 }
 
 template <class PL, int MINB>
@@ -337,6 +360,7 @@ PlanOps make_ops()
     o.fill_twiddles = &fill_twiddles_impl<PL>;
     o.prepare = &prepare_impl<PL, MINB>;
     o.launch = &launch_impl<PL, MINB>;
+    o.launch_fused = PL::SH > 1 ? &launch_fused_impl<PL, MINB> : nullptr;
     return o;
 }
 
@@ -437,7 +461,8 @@ struct ChanState {
     float* hsqrd = nullptr;           // [frames][K]
     float* epart = nullptr;           // [frames + kPilotCtaTarget][N]
     unsigned int* counters = nullptr; // [frames], zero between launches
-    unsigned long long* ticket = nullptr;  // data-kernel work-item counter + departed-CTA counter, self-resetting
+    unsigned long long* ticket = nullptr;  // data-kernel work-item counter + departed-CTA counter (self-resetting), [2] launch number of the fused kernel
+    unsigned int* ready = nullptr;         // [frames] fused kernel: launch number that last completed the frame's channel state
     int frames = 0;
 };
 constexpr int kPilotCtaTarget = 4096;  // upper bound on frames*groups - frames (epart scratch rows)
@@ -488,6 +513,8 @@ struct lsmrc_ctx {
     long long oneshot_calls = 0;  // batches served by the one-launch kernel
     long long zero_copy_calls = 0;  // ... of which on pinned host buffers in place
     bool oneshot = true;
+    bool one_launch_frames = true;  // shuffle-stage plans: pilot and data items of large batches in one persistent launch (lsmrc_frames_sh)
+    long long fused_calls = 0;
     bool zero_copy = true;        // one-launch kernel reads/writes pinned host buffers in place (small frames)
     bool h2d_strip_cp = true;     // lsmrc_demod_frames_host: strided H2D copy that leaves the cyclic prefix behind
     size_t h2d_strip_min_row = 512;   // ... for rows of at least this many bytes (LSMRC_H2D_STRIP_MIN_ROW, 0 = off);
@@ -581,6 +608,7 @@ int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
     cudaFree(c.epart);
     cudaFree(c.counters);
     cudaFree(c.ticket);
+    cudaFree(c.ready);
     c = ChanState();
     const size_t N = (size_t)h->cfg.fft_size;
     CK(h, cudaMalloc(&c.hwork, (size_t)frames * h->cfg.n_ant * N * sizeof(float2)));
@@ -588,8 +616,10 @@ int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
     CK(h, cudaMalloc(&c.epart, ((size_t)frames + kPilotCtaTarget) * N * sizeof(float)));
     CK(h, cudaMalloc(&c.counters, (size_t)frames * sizeof(unsigned int)));
     CK(h, cudaMemset(c.counters, 0, (size_t)frames * sizeof(unsigned int)));
-    CK(h, cudaMalloc(&c.ticket, 2 * sizeof(unsigned long long)));
-    CK(h, cudaMemset(c.ticket, 0, 2 * sizeof(unsigned long long)));
+    CK(h, cudaMalloc(&c.ticket, 4 * sizeof(unsigned long long)));
+    CK(h, cudaMemset(c.ticket, 0, 4 * sizeof(unsigned long long)));
+    CK(h, cudaMalloc(&c.ready, (size_t)frames * sizeof(unsigned int)));
+    CK(h, cudaMemset(c.ready, 0, (size_t)frames * sizeof(unsigned int)));
     // the memsets run on the legacy stream, the kernels on non-blocking streams that do not order against it
     CK(h, cudaDeviceSynchronize());
     c.frames = frames;
@@ -599,6 +629,7 @@ int ensure_chan(lsmrc_ctx* h, ChanState& c, int frames, cudaStream_t quiesce)
 void free_chan(ChanState& c)
 {
     cudaFree(c.ticket);
+    cudaFree(c.ready);
     cudaFree(c.hwork);
     cudaFree(c.hsqrd);
     cudaFree(c.epart);
@@ -680,6 +711,38 @@ int launch_data(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, fl
     return LSMRC_OK;
 }
 
+// Shuffle-stage plans, batches that give every team of a full wave of CTAs its own (frame, symbol) pair: pilot items, then
+// data items, from one persistent launch (lsmrc_frames_sh).  Returns 1 when it launched, 0 when the kernel pair has to run.
+int launch_fused(lsmrc_ctx* h, cudaStream_t st, KernelParams p, ChanState& ch, float2* d_hconj, float* d_hsqrd, cudaEvent_t ev_before)
+{
+    const lsmrc_config& c = h->cfg;
+    if (!h->ops->launch_fused || !h->one_launch_frames || h->pilot_ops || c.n_sym < 2) return 0;
+    const int teams = h->ops->teams;
+    const long long n_work = (long long)p.n_frames * (c.n_sym - 1);
+    if ((n_work + teams - 1) / teams < (long long)h->max_data_ctas) return 0;  // (smaller batches: antenna split / wider pilot grid)
+    p.n_groups = pilot_groups(h, p.n_frames);
+    if (p.n_groups == 1 && h->pilot_teams / c.n_ant > 1) return 0;             // (few antennas: the pilot kernel packs frames)
+    p.first_sym = 1;
+    p.n_sym_work = c.n_sym - 1;
+    p.hwork = ch.hwork;
+    p.hconj = d_hconj;
+    p.hsqrd = d_hsqrd ? d_hsqrd : ch.hsqrd;
+    p.frames_per_cta = 1;
+    p.pilot_grid_cap = 0;
+    p.epart = ch.epart;
+    p.counters = ch.counters;
+    p.ticket = ch.ticket;
+    p.ready = ch.ready;
+    p.ant_split = 1;
+    p.x_tma = (reinterpret_cast<uintptr_t>(p.rx) % 16 == 0) && p.cp % 2 == 0 && p.ant_stride % 2 == 0 && p.sym_stride % 2 == 0 &&
+              p.frame_stride % 2 == 0;
+    if (ev_before) CK(h, cudaEventRecord(ev_before, st));  // (no separate pilot phase: the split reported is 0 / whole)
+    CK(h, h->ops->launch_fused(p, st, h->max_data_ctas));
+    h->launches++;
+    h->fused_calls++;
+    return 1;
+}
+
 // where the symbols of ONE frame sit when they are not a dense [S][A][N+C] block (ring slots read in place)
 struct RxLayout {
     long long sym_stride;  // complex elements between consecutive symbols
@@ -739,7 +802,16 @@ int launch_frames(lsmrc_ctx* h, cudaStream_t st, const float2* d_rx, int n_frame
         return LSMRC_OK;
     }
     if (lay) return fail(h, LSMRC_ERR_STATE, "in-place ring layout without the one-launch kernel");
-    int rc = launch_pilot(h, st, p, ch, d_hconj, d_hsqrd);
+    int rc = launch_fused(h, st, p, ch, d_hconj, d_hsqrd, timed ? ev[1] : nullptr);
+    if (rc < 0) return rc;
+    if (rc == 1) {  // channel estimate and data symbols of the whole batch went out as one persistent launch
+        if (timed) {
+            CK(h, cudaEventRecord(ev[2], st));
+            h->ev_calls++;
+        }
+        return LSMRC_OK;
+    }
+    rc = launch_pilot(h, st, p, ch, d_hconj, d_hsqrd);
     if (rc != LSMRC_OK) return rc;
     if (timed) CK(h, cudaEventRecord(ev[1], st));
     if (h->cfg.n_sym > 1) {
@@ -1898,6 +1970,15 @@ int lsmrc_set_oneshot(lsmrc_handle h, int enabled)
 }
 
 long long lsmrc_oneshot_count(lsmrc_handle h) { return h ? h->oneshot_calls : -1; }
+
+int lsmrc_set_one_launch_frames(lsmrc_handle h, int enabled)
+{
+    if (!h) return LSMRC_ERR_INVALID;
+    h->one_launch_frames = enabled != 0;
+    return LSMRC_OK;
+}
+
+long long lsmrc_one_launch_frames_count(lsmrc_handle h) { return h ? h->fused_calls : -1; }
 
 int lsmrc_set_timing(lsmrc_handle h, int enabled)
 {

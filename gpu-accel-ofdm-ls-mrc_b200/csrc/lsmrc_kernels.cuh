@@ -88,6 +88,9 @@ struct KernelParams {
     // that have drawn their last ticket.  Both are zero between launches: the last CTA to leave resets them, so a
     // launch carries no host-side state (safe to replay from a CUDA graph or to move between streams).
     unsigned long long* ticket;
+    // single-launch kernel of the shuffle-stage plans (lsmrc_frames_sh): ready[f] = launch number (ticket[2] + 1) once frame
+    // f's channel state is complete
+    unsigned int* ready;
     // data kernel, plans without the Hconj ring: antennas of one (frame, symbol) are split over
     // ant_split teams of the CTA (power of two, <= TEAMS) whose partial sums are added in shared
     // memory -- used when there are too few (frame, symbol) pairs to fill the GPU (latency configs)
@@ -802,7 +805,7 @@ __device__ __forceinline__ void row_fft(float2 (&v)[PL::P], const float2* __rest
 // the bin the thread owns in slot sl; e_row[bin - 1] = sum_a |H|^2 (global, or shared when
 // E_SHARED).  Specialised on the QAM order so the demapper and the bit packing are straight-line
 // code.  s_idx: K bytes of team-private shared memory (aliases the team's tile).
-template <class PL, bool E_SHARED>
+template <class PL, bool E_SHARED, bool E_CG = false>
 __device__ __forceinline__ void mrc_finish(const KernelParams& p, const float2 (&acc)[PL::P], const float* __restrict__ e_row,
                                            int f, int s, uint8_t* s_idx, bool valid, int t, int team)
 {
@@ -817,7 +820,7 @@ __device__ __forceinline__ void mrc_finish(const KernelParams& p, const float2 (
         for (int sl = 0; sl < P; ++sl) {
             const int bin = PL::bin_of(sl, t);
             const int idx = bin > 0 ? bin - 1 : 0;
-            einv[sl] = E_SHARED ? e_row[idx] : __ldg(e_row + idx);
+            einv[sl] = E_SHARED ? e_row[idx] : (E_CG ? __ldcg(e_row + idx) : __ldg(e_row + idx));  // E_CG: written during this launch
         }
         team_sync<PL>(team);  // everyone is done reading the last tile before it is reused
 #pragma unroll
@@ -1383,6 +1386,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
     }
 }
 
+constexpr int kShTmemCols = 128;  // tensor-memory columns per CTA of the shuffle-stage kernels: both twiddle sets of a thread
+
 // ---- row pipeline shared by the two kernels of the shuffle-stage plans -----------------------------------------
 // Per-team state of the pipeline in shared memory / tensor memory.
 template <class PL>
@@ -1486,30 +1491,87 @@ __device__ __forceinline__ void sh_fill_tmem(uint32_t tmem, const float2* __rest
 //    neither shared-memory wavefronts (a table) nor fp32 instructions (a recurrence).
 // Shared memory per CTA: TEAMS x (channel row N + tile N) complex = 64 KB -> 3 CTAs per SM.
 // Rows that are not 16-byte aligned (odd prefix lengths) are read with plain 64-bit loads instead of bulk copies.
-template <class PL, int MINB>
-__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelParams p)
+// One work item of the data kernel: TEAMS consecutive (frame, data symbol) pairs, one per team, all antennas.
+// E_CG: sum|H|^2 is read around L1 (the fused kernel: it was written by another CTA of the same launch).
+template <class PL, bool E_CG>
+__device__ __forceinline__ void sh_data_item(const KernelParams& p, ShRow<PL>& row, float2* hbuf, uint64_t* bar_h, uint32_t& h_phase, int item)
 {
-    constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, ROW = PL::ROW, TEAMS = PL::TEAMS;
-    constexpr int WPT = T / 32;  // warps per team
+    constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, TEAMS = PL::TEAMS;
     constexpr uint32_t ROW_BYTES = N * sizeof(float2);
-    static_assert(SH > 1 && ROW == T, "shuffle-stage plans only");
-    extern __shared__ __align__(16) float2 smem[];
-    float2* s_h = smem;                     // [TEAMS][N]   conj(H) of the current antenna, slot-major
-    float2* s_tiles = s_h + TEAMS * N;      // [TEAMS][32][T]
-    __shared__ __align__(8) uint64_t bar_x[TEAMS], bar_h[TEAMS];
-    __shared__ unsigned int s_readers[TEAMS];  // warps of the team that have read their stage-2 operands of this row
-    __shared__ int s_item;
+    const int t = row.t, team = row.team, q = row.q;
+    const uint32_t tmem = row.tmem;
+    const long long n_work = (long long)p.n_frames * p.n_sym_work;
+    long long work = (long long)item * TEAMS + team;
+    bool valid = work < n_work;
+    if (!valid) work = n_work - 1;
+    const int f = (int)(work / p.n_sym_work);
+    const int s = (int)(work % p.n_sym_work);
+    const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)(p.first_sym + s) * p.sym_stride + p.cp;
+    const float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+    float2 acc[32];
+#pragma unroll
+    for (int sl = 0; sl < 32; ++sl) acc[sl] = make_float2(0.f, 0.f);
 
+    if (row.x_tma && t == 0) sh_fetch_row<PL>(row, x0);  // (the tile doubled as the previous item's demap byte buffer)
+    for (int a = 0; a < p.n_ant; ++a) {
+        const float2* x_row = x0 + (long long)a * p.ant_stride;
+        float2 v[32];
+        sh_row_front<PL>(row, v, x_row, a + 1 < p.n_ant ? x_row + p.ant_stride : nullptr, [&]() {
+            // every warp of the team is past the previous antenna: its channel row may be replaced
+            if (t == 0) {
+                mbar_expect_tx(bar_h, ROW_BYTES);
+                bulk_g2s_hint(hbuf, hw_frame + (long long)a * N, ROW_BYTES, bar_h, l2_policy_evict_last());
+            }
+        });
+        // ---- twiddle W_T^(q*k2), radix-SH across the lanes, multiply-accumulate with conj(H)
+        constexpr int JB = kShBatch;
+        pin_values(v);  // the stage-2 transform stays ahead of the wait: it is the time the channel row has to land
+        mbar_wait(bar_h, h_phase);
+        h_phase ^= 1u;
+#pragma unroll
+        for (int c = 0; c < 16 / JB; ++c) {
+            float2 tw[2 * JB], h[2 * JB];
+            tmem_load8(tmem, 64 + 16 * c, tw);
+#pragma unroll
+            for (int i = 0; i < 2 * JB; ++i) h[i] = lds_volatile(hbuf + (2 * JB * c + i) * T + t);
+            asm volatile("" ::: "memory");
+            float2 keep[JB], send[JB], A[JB], B[JB];
+#pragma unroll
+            for (int i = 0; i < JB; ++i) {
+                keep[i] = cmul(v[2 * (JB * c + i)], tw[2 * i]);
+                send[i] = cmul(v[2 * (JB * c + i) + 1], tw[2 * i + 1]);
+            }
+            sh_radix_batch<SH, JB>(keep, send, q, A, B);
+            // cpuLS.hpp:187-208: acc += Y * Hconj (both carry the slot's unit factor: it cancels)
+#pragma unroll
+            for (int i = 0; i < JB; ++i) {
+                const int sl = 2 * (JB * c + i);
+                acc[sl] = cmac(acc[sl], h[2 * i], A[i]);
+                acc[sl + 1] = cmac(acc[sl + 1], h[2 * i + 1], B[i]);
+            }
+        }
+    }
+    team_sync<PL>(team);  // every warp is done with the last row before the tile becomes the demap byte buffer
+    mrc_finish<PL, false, E_CG>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(row.tile), valid, t, team);
+    team_sync<PL>(team);  // the byte buffer aliases the tile the next item's first row is copied into
+}
+
+// per-CTA set-up shared by the kernels of the shuffle-stage plans: barriers, the reader counters, both twiddle sets into
+// this thread's tensor-memory lane (columns [0, 64) the 32 stage-1 factors stage1_sign(t) * W_N^(t*r), columns [64, 128)
+// the 32 factors W_T^(q*k2) of its stage-2 registers), and the per-team pipeline state
+template <class PL>
+__device__ __forceinline__ void sh_setup(const KernelParams& p, ShRow<PL>& row, float2* s_tiles, uint64_t* bar_x, uint64_t* bar_h,
+                                         unsigned int* s_readers, uint32_t* s_tmem)
+{
+    constexpr int T = PL::T, SH = PL::SH, TEAMS = PL::TEAMS, N = PL::N;
+    static_assert(PL::THREADS == 128, "one tensor-memory lane per thread: CTAs of exactly four warps");
     const int team = threadIdx.x / T;
     const int t = threadIdx.x % T;
     const int lane = t & 31, wt = t >> 5;
-    float2* tile = s_tiles + team * N;
-    float2* hbuf = s_h + team * N;
-
     if (threadIdx.x == 0) {
         for (int i = 0; i < TEAMS; ++i) {
             mbar_init(&bar_x[i], 1);
-            mbar_init(&bar_h[i], 1);
+            if (bar_h) mbar_init(&bar_h[i], 1);
             s_readers[i] = 0u;
         }
         mbar_fence_init();
@@ -1517,99 +1579,67 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
     // this thread's stage-2 role: row k1 of the tile, lane position q of the shuffle group
     const int q = lane % SH;
     const int k1 = lane / SH + (32 / SH) * wt;
-    // Both twiddle sets of this thread go to its tensor-memory lane once: columns [0, 64) the 32 stage-1 factors
-    // stage1_sign(t) * W_N^(t*r) (r = 0: just the sign), columns [64, 128) the 32 factors W_T^(q*k2) of its stage-2
-    // registers (k2 as in sh_radix_batch).
-    static_assert(PL::THREADS == 128, "one tensor-memory lane per thread: CTAs of exactly four warps");
-    constexpr int kTmemCols = 128;
-    __shared__ uint32_t s_tmem;
-    const uint32_t tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+    const uint32_t tmem = tmem_alloc_cols(s_tmem, kShTmemCols, (int)(threadIdx.x >> 5));
     sh_fill_tmem<PL>(tmem, p.twiddles, t, q);
-    __syncthreads();
-
-    const long long n_work = (long long)p.n_frames * p.n_sym_work;
-    const int n_items = (int)((n_work + TEAMS - 1) / TEAMS);
-    ShRow<PL> row;
-    row.tile = tile;
+    row.tile = s_tiles + team * N;
     row.bar_x = &bar_x[team];
     row.readers = &s_readers[team];
     row.tmem = tmem;
     row.x_phase = 0;
     row.x_tma = p.x_tma != 0;
     row.t = t, row.lane = lane, row.wt = wt, row.team = team, row.q = q, row.k1 = k1;
-    uint32_t h_phase = 0;
+}
 
-    for (;;) {
-        if (threadIdx.x == 0) {
-            const unsigned long long tk = atomicAdd(p.ticket, 1ULL);
-            s_item = tk < (unsigned long long)n_items ? (int)tk : -1;
-            if (s_item < 0) {
-                __threadfence();
-                if (atomicAdd(p.ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
-                    p.ticket[0] = 0ULL;
-                    p.ticket[1] = 0ULL;
-                }
+// draws the next ticket of a persistent kernel (thread 0) and hands it to the whole CTA; -1 when the launch has run out
+// of its n_tickets.  The last CTA to find the counter exhausted re-arms it for the next launch (and, when `epoch` is
+// given, advances the launch number that the fused kernel's ready flags carry).
+template <class F>
+__device__ __forceinline__ long long draw_ticket(const KernelParams& p, long long n_tickets, long long* s_ticket, bool with_epoch, F&& decode)
+{
+    if (threadIdx.x == 0) {
+        const unsigned long long tk = atomicAdd(p.ticket, 1ULL);
+        *s_ticket = tk < (unsigned long long)n_tickets ? (long long)tk : -1;
+        if (*s_ticket >= 0) decode((long long)tk);  // (thread 0 only: whatever the CTA needs to know about the ticket, via shared memory)
+        if (*s_ticket < 0) {
+            __threadfence();
+            if (atomicAdd(p.ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+                if (with_epoch) p.ticket[2] = p.ticket[2] + 1ULL;
+                p.ticket[0] = 0ULL;
+                p.ticket[1] = 0ULL;
             }
         }
-        __syncthreads();
-        const int item = s_item;
-        __syncthreads();
-        if (item < 0) break;
-        long long work = (long long)item * TEAMS + team;
-        bool valid = work < n_work;
-        if (!valid) work = n_work - 1;
-        const int f = (int)(work / p.n_sym_work);
-        const int s = (int)(work % p.n_sym_work);
-        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)(p.first_sym + s) * p.sym_stride + p.cp;
-        const float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
-        float2 acc[32];
-#pragma unroll
-        for (int sl = 0; sl < 32; ++sl) acc[sl] = make_float2(0.f, 0.f);
-
-        if (row.x_tma && t == 0) sh_fetch_row<PL>(row, x0);  // (the tile doubled as the previous item's demap byte buffer)
-        for (int a = 0; a < p.n_ant; ++a) {
-            const float2* x_row = x0 + (long long)a * p.ant_stride;
-            float2 v[32];
-            sh_row_front<PL>(row, v, x_row, a + 1 < p.n_ant ? x_row + p.ant_stride : nullptr, [&]() {
-                // every warp of the team is past the previous antenna: its channel row may be replaced
-                if (t == 0) {
-                    mbar_expect_tx(&bar_h[team], ROW_BYTES);
-                    bulk_g2s_hint(hbuf, hw_frame + (long long)a * N, ROW_BYTES, &bar_h[team], l2_policy_evict_last());
-                }
-            });
-            // ---- twiddle W_T^(q*k2), radix-SH across the lanes, multiply-accumulate with conj(H)
-            constexpr int JB = kShBatch;
-            pin_values(v);  // the stage-2 transform stays ahead of the wait: it is the time the channel row has to land
-            mbar_wait(&bar_h[team], h_phase);
-            h_phase ^= 1u;
-#pragma unroll
-            for (int c = 0; c < 16 / JB; ++c) {
-                float2 tw[2 * JB], h[2 * JB];
-                tmem_load8(tmem, 64 + 16 * c, tw);
-#pragma unroll
-                for (int i = 0; i < 2 * JB; ++i) h[i] = lds_volatile(hbuf + (2 * JB * c + i) * T + t);
-                asm volatile("" ::: "memory");
-                float2 keep[JB], send[JB], A[JB], B[JB];
-#pragma unroll
-                for (int i = 0; i < JB; ++i) {
-                    keep[i] = cmul(v[2 * (JB * c + i)], tw[2 * i]);
-                    send[i] = cmul(v[2 * (JB * c + i) + 1], tw[2 * i + 1]);
-                }
-                sh_radix_batch<SH, JB>(keep, send, q, A, B);
-                // cpuLS.hpp:187-208: acc += Y * Hconj (both carry the slot's unit factor: it cancels)
-#pragma unroll
-                for (int i = 0; i < JB; ++i) {
-                    const int sl = 2 * (JB * c + i);
-                    acc[sl] = cmac(acc[sl], h[2 * i], A[i]);
-                    acc[sl + 1] = cmac(acc[sl + 1], h[2 * i + 1], B[i]);
-                }
-            }
-        }
-        team_sync<PL>(team);  // every warp is done with the last row before the tile becomes the demap byte buffer
-        mrc_finish<PL, false>(p, acc, p.hsqrd + (long long)f * K, f, s, reinterpret_cast<uint8_t*>(tile), valid, t, team);
-        team_sync<PL>(team);  // the byte buffer aliases the tile the next item's first row is copied into
     }
-    tmem_free_cols(s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+    __syncthreads();
+    const long long tk = *s_ticket;
+    __syncthreads();  // s_ticket is rewritten by thread 0 at the top of the next round
+    return tk;
+}
+
+template <class PL, int MINB>
+__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelParams p)
+{
+    constexpr int N = PL::N, TEAMS = PL::TEAMS;
+    static_assert(PL::SH > 1 && PL::ROW == PL::T, "shuffle-stage plans only");
+    extern __shared__ __align__(16) float2 smem[];
+    float2* s_h = smem;                     // [TEAMS][N]   conj(H) of the current antenna, slot-major
+    float2* s_tiles = s_h + TEAMS * N;      // [TEAMS][32][T]
+    __shared__ __align__(8) uint64_t bar_x[TEAMS], bar_h[TEAMS];
+    __shared__ unsigned int s_readers[TEAMS];  // warps of the team that have read their stage-2 operands of this row
+    __shared__ long long s_ticket;
+    __shared__ uint32_t s_tmem;
+    ShRow<PL> row;
+    sh_setup<PL>(p, row, s_tiles, bar_x, bar_h, s_readers, &s_tmem);
+    __syncthreads();
+
+    const long long n_work = (long long)p.n_frames * p.n_sym_work;
+    const long long n_items = (n_work + TEAMS - 1) / TEAMS;
+    uint32_t h_phase = 0;
+    for (;;) {
+        const long long item = draw_ticket(p, n_items, &s_ticket, false, [](long long) {});
+        if (item < 0) break;
+        sh_data_item<PL, false>(p, row, s_h + row.team * N, &bar_h[row.team], h_phase, (int)item);
+    }
+    tmem_free_cols(s_tmem, kShTmemCols, (int)(threadIdx.x >> 5));
 }
 
 // ---- pilot kernel of the shuffle-stage plans -----------------------------------------------------------------
@@ -1621,34 +1651,13 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_data_sh(const KernelP
 // slot-major shared table where the data kernel keeps its channel row, and each thread reads its own 32 entries.
 // conj(H) goes to hwork slot-major and factored exactly as the data kernel's outputs are (Plan::unit_mul), so the
 // store is coalesced and needs no fix-up; the optional Hconj export in the reference layout is corrected.
-template <class PL, int MINB>
-__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_pilot_sh(const KernelParams p)
+// the LS-divide table of a CTA: g = conj(X)/|X|^2 per (slot, thread), slot-major like a channel row; entry of bin 0 is zero
+template <class PL>
+__device__ __forceinline__ void sh_fill_g(const KernelParams& p, float2* s_g)
 {
-    constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, TEAMS = PL::TEAMS;
-    static_assert(SH > 1 && PL::ROW == T && PL::THREADS == 128, "shuffle-stage plans only");
-    extern __shared__ __align__(16) float2 smem[];
-    float2* s_g = smem;                 // [32][T] conj(X)/|X|^2 of (slot, thread); entry of bin 0 is zero
-    float2* s_tiles = s_g + N;          // [TEAMS][32][T]
-    __shared__ __align__(8) uint64_t bar_x[TEAMS];
-    __shared__ unsigned int s_readers[TEAMS];
-    __shared__ uint32_t s_tmem;
-    __shared__ unsigned int s_last;
-
-    const int team = threadIdx.x / T;
-    const int t = threadIdx.x % T;
-    const int lane = t & 31, wt = t >> 5;
-    const int q = lane % SH;
-    const int k1 = lane / SH + (32 / SH) * wt;
-    float2* tile = s_tiles + team * N;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < TEAMS; ++i) {
-            mbar_init(&bar_x[i], 1);
-            s_readers[i] = 0u;
-        }
-        mbar_fence_init();
-    }
-    if (team == 0) {
+    constexpr int T = PL::T;
+    if (threadIdx.x < T) {
+        const int t = threadIdx.x;
 #pragma unroll
         for (int sl = 0; sl < 32; ++sl) {
             const int bin = PL::bin_of(sl, t);
@@ -1661,116 +1670,221 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_pilot_sh(const Kernel
             s_g[sl * T + t] = g;
         }
     }
-    constexpr int kTmemCols = 128;
-    const uint32_t tmem = tmem_alloc_cols(&s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
-    sh_fill_tmem<PL>(tmem, p.twiddles, t, q);
-    __syncthreads();
+}
 
-    ShRow<PL> row;
-    row.tile = tile;
-    row.bar_x = &bar_x[team];
-    row.readers = &s_readers[team];
-    row.tmem = tmem;
-    row.x_phase = 0;
-    row.x_tma = p.x_tma != 0;
-    row.t = t, row.lane = lane, row.wt = wt, row.team = team, row.q = q, row.k1 = k1;
-
+// One virtual CTA of the pilot kernel: antenna group g of frame f (vb = f * n_groups + g), pilot symbol `sym`.
+// Returns true in every thread when this call completed the frame's channel state (all of hwork and sum|H|^2 written:
+// the only group, or the last group to arrive).
+template <class PL>
+__device__ __forceinline__ bool sh_pilot_item(const KernelParams& p, ShRow<PL>& row, const float2* s_g, float2* s_tiles, unsigned int* s_last,
+                                              int vb, int sym)
+{
+    constexpr int N = PL::N, T = PL::T, K = N - 1, SH = PL::SH, TEAMS = PL::TEAMS;
+    const int t = row.t, team = row.team, q = row.q;
+    const uint32_t tmem = row.tmem;
     const int per_iter = p.n_groups * TEAMS;
     const int n_iter = (p.n_ant + per_iter - 1) / per_iter;
-    const int n_virtual = p.n_frames * p.n_groups;
-    for (int vb = blockIdx.x; vb < n_virtual; vb += gridDim.x) {
-        const int f = vb / p.n_groups;
-        const int g = vb % p.n_groups;
-        const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)p.first_sym * p.sym_stride + p.cp;
-        float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
-        float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
-        float e[32];
+    const int f = vb / p.n_groups;
+    const int g = vb % p.n_groups;
+    const float2* x0 = p.rx + (long long)f * p.frame_stride + (long long)sym * p.sym_stride + p.cp;
+    float2* hw_frame = p.hwork + (long long)f * p.n_ant * N;
+    float2* hc_frame = p.hconj ? p.hconj + (long long)f * p.n_ant * K : nullptr;
+    float e[32];
 #pragma unroll
-        for (int sl = 0; sl < 32; ++sl) e[sl] = 0.f;
-        // antenna of this team in iteration `it`; teams whose share has run out redo the last antenna and drop it
-        auto ant_of = [&](int it) { return (it * p.n_groups + g) * TEAMS + team; };
-        auto row_of = [&](int it) {
-            const int a = ant_of(it);
-            return x0 + (long long)(a < p.n_ant ? a : p.n_ant - 1) * p.ant_stride;
-        };
-        if (row.x_tma && t == 0) sh_fetch_row<PL>(row, row_of(0));
-        for (int it = 0; it < n_iter; ++it) {
-            const int a_raw = ant_of(it);
-            const bool a_ok = a_raw < p.n_ant;
-            const int a = a_ok ? a_raw : p.n_ant - 1;
-            float2 v[32];
-            sh_row_front<PL>(row, v, row_of(it), it + 1 < n_iter ? row_of(it + 1) : nullptr, []() {});
-            float2* hw_row = hw_frame + (long long)a * N + t;
-            float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
-            constexpr int JB = kShBatch;
+    for (int sl = 0; sl < 32; ++sl) e[sl] = 0.f;
+    // antenna of this team in iteration `it`; teams whose share has run out redo the last antenna and drop it
+    auto ant_of = [&](int it) { return (it * p.n_groups + g) * TEAMS + team; };
+    auto row_of = [&](int it) {
+        const int a = ant_of(it);
+        return x0 + (long long)(a < p.n_ant ? a : p.n_ant - 1) * p.ant_stride;
+    };
+    if (row.x_tma && t == 0) sh_fetch_row<PL>(row, row_of(0));
+    for (int it = 0; it < n_iter; ++it) {
+        const int a_raw = ant_of(it);
+        const bool a_ok = a_raw < p.n_ant;
+        const int a = a_ok ? a_raw : p.n_ant - 1;
+        float2 v[32];
+        sh_row_front<PL>(row, v, row_of(it), it + 1 < n_iter ? row_of(it + 1) : nullptr, []() {});
+        float2* hw_row = hw_frame + (long long)a * N + t;
+        float2* hc_row = hc_frame ? hc_frame + (long long)a * K : nullptr;
+        constexpr int JB = kShBatch;
 #pragma unroll
-            for (int c = 0; c < 16 / JB; ++c) {
-                float2 tw[2 * JB], gk[2 * JB];
-                tmem_load8(tmem, 64 + 16 * c, tw);
+        for (int c = 0; c < 16 / JB; ++c) {
+            float2 tw[2 * JB], gk[2 * JB];
+            tmem_load8(tmem, 64 + 16 * c, tw);
 #pragma unroll
-                for (int i = 0; i < 2 * JB; ++i) gk[i] = s_g[(2 * JB * c + i) * T + t];
-                float2 keep[JB], send[JB], A[JB], B[JB];
+            for (int i = 0; i < 2 * JB; ++i) gk[i] = s_g[(2 * JB * c + i) * T + t];
+            float2 keep[JB], send[JB], A[JB], B[JB];
 #pragma unroll
-                for (int i = 0; i < JB; ++i) {
-                    keep[i] = cmul(v[2 * (JB * c + i)], tw[2 * i]);
-                    send[i] = cmul(v[2 * (JB * c + i) + 1], tw[2 * i + 1]);
-                }
-                sh_radix_batch<SH, JB>(keep, send, q, A, B);
+            for (int i = 0; i < JB; ++i) {
+                keep[i] = cmul(v[2 * (JB * c + i)], tw[2 * i]);
+                send[i] = cmul(v[2 * (JB * c + i) + 1], tw[2 * i + 1]);
+            }
+            sh_radix_batch<SH, JB>(keep, send, q, A, B);
 #pragma unroll
-                for (int i = 0; i < 2 * JB; ++i) {
-                    const int sl = 2 * JB * c + i;
-                    const float2 z = (i & 1) ? B[i / 2] : A[i / 2];
-                    // LS estimate H = Z / X (cpuLS.hpp:233-244) as Z * conj(X)/|X|^2, then conj (:303-307); z, and so
-                    // hc, carry the slot's unit factor, the energy does not care
-                    const float re = z.x * gk[i].x - z.y * gk[i].y;
-                    const float im = z.x * gk[i].y + z.y * gk[i].x;
-                    if (a_ok) {
-                        const float2 hc = make_float2(re, -im);
-                        hw_row[sl * T] = hc;
-                        if (hc_row) {
-                            const int bin = PL::bin_of(sl, t);
-                            if (bin > 0) hc_row[bin - 1] = PL::refix(sl, t, hc);
-                        }
-                        e[sl] += re * re + im * im;  // cpuLS.hpp:211-228 (the entry of bin 0 is zero)
+            for (int i = 0; i < 2 * JB; ++i) {
+                const int sl = 2 * JB * c + i;
+                const float2 z = (i & 1) ? B[i / 2] : A[i / 2];
+                // LS estimate H = Z / X (cpuLS.hpp:233-244) as Z * conj(X)/|X|^2, then conj (:303-307); z, and so
+                // hc, carry the slot's unit factor, the energy does not care
+                const float re = z.x * gk[i].x - z.y * gk[i].y;
+                const float im = z.x * gk[i].y + z.y * gk[i].x;
+                if (a_ok) {
+                    const float2 hc = make_float2(re, -im);
+                    hw_row[sl * T] = hc;
+                    if (hc_row) {
+                        const int bin = PL::bin_of(sl, t);
+                        if (bin > 0) hc_row[bin - 1] = PL::refix(sl, t, hc);
                     }
+                    e[sl] += re * re + im * im;  // cpuLS.hpp:211-228 (the entry of bin 0 is zero)
                 }
             }
         }
-        // deterministic cross-team sum of the energy partials, then cross-group by the last CTA of the frame
-        __syncthreads();
-        float* s_e = reinterpret_cast<float*>(s_tiles);  // [TEAMS][N] indexed by bin; aliases the tiles (no copy is in flight)
-#pragma unroll
-        for (int sl = 0; sl < 32; ++sl) s_e[team * N + PL::bin_of(sl, t)] = e[sl];
-        __syncthreads();
-        for (int bin = 1 + (int)threadIdx.x; bin < N; bin += PL::THREADS) {
-            float acc = s_e[bin];
-#pragma unroll
-            for (int tm = 1; tm < TEAMS; ++tm) acc += s_e[tm * N + bin];
-            float* dst = (p.n_groups == 1) ? (p.hsqrd + (long long)f * K - 1) : (p.epart + ((long long)f * p.n_groups + g) * N);
-            dst[bin] = acc;
-        }
-        if (p.n_groups > 1) {
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const unsigned int prev = atomicAdd(p.counters + f, 1u);
-                s_last = (prev == (unsigned)p.n_groups - 1u);
-                if (s_last) p.counters[f] = 0u;  // self-reset for the next launch
-            }
-            __syncthreads();
-            if (s_last) {
-                __threadfence();
-                const float* ep = p.epart + (long long)f * p.n_groups * N;
-                for (int bin = 1 + (int)threadIdx.x; bin < N; bin += PL::THREADS) {
-                    float acc = __ldcg(ep + bin);
-                    for (int gg = 1; gg < p.n_groups; ++gg) acc += __ldcg(ep + (long long)gg * N + bin);
-                    p.hsqrd[(long long)f * K + bin - 1] = acc;
-                }
-            }
-        }
-        __syncthreads();  // the partial-energy buffer aliases the tiles the next virtual CTA copies into
     }
-    tmem_free_cols(s_tmem, kTmemCols, (int)(threadIdx.x >> 5));
+    // deterministic cross-team sum of the energy partials, then cross-group by the last CTA of the frame
+    __syncthreads();
+    float* s_e = reinterpret_cast<float*>(s_tiles);  // [TEAMS][N] indexed by bin; aliases the tiles (no copy is in flight)
+#pragma unroll
+    for (int sl = 0; sl < 32; ++sl) s_e[team * N + PL::bin_of(sl, t)] = e[sl];
+    __syncthreads();
+    for (int bin = 1 + (int)threadIdx.x; bin < N; bin += PL::THREADS) {
+        float acc = s_e[bin];
+#pragma unroll
+        for (int tm = 1; tm < TEAMS; ++tm) acc += s_e[tm * N + bin];
+        float* dst = (p.n_groups == 1) ? (p.hsqrd + (long long)f * K - 1) : (p.epart + ((long long)f * p.n_groups + g) * N);
+        dst[bin] = acc;
+    }
+    bool completed = p.n_groups == 1;
+    if (p.n_groups > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(p.counters + f, 1u);
+            *s_last = (prev == (unsigned)p.n_groups - 1u);
+            if (*s_last) p.counters[f] = 0u;  // self-reset for the next launch
+        }
+        __syncthreads();
+        if (*s_last) {
+            __threadfence();
+            const float* ep = p.epart + (long long)f * p.n_groups * N;
+            for (int bin = 1 + (int)threadIdx.x; bin < N; bin += PL::THREADS) {
+                float acc = __ldcg(ep + bin);
+                for (int gg = 1; gg < p.n_groups; ++gg) acc += __ldcg(ep + (long long)gg * N + bin);
+                p.hsqrd[(long long)f * K + bin - 1] = acc;
+            }
+            completed = true;
+        }
+    }
+    __syncthreads();  // the partial-energy buffer aliases the tiles the next virtual CTA copies into
+    return completed;
+}
+
+template <class PL, int MINB>
+__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_pilot_sh(const KernelParams p)
+{
+    constexpr int N = PL::N, TEAMS = PL::TEAMS;
+    static_assert(PL::SH > 1 && PL::ROW == PL::T && PL::THREADS == 128, "shuffle-stage plans only");
+    extern __shared__ __align__(16) float2 smem[];
+    float2* s_g = smem;                 // [32][T] conj(X)/|X|^2 of (slot, thread)
+    float2* s_tiles = s_g + N;          // [TEAMS][32][T]
+    __shared__ __align__(8) uint64_t bar_x[TEAMS];
+    __shared__ unsigned int s_readers[TEAMS];
+    __shared__ uint32_t s_tmem;
+    __shared__ unsigned int s_last;
+    ShRow<PL> row;
+    sh_setup<PL>(p, row, s_tiles, bar_x, nullptr, s_readers, &s_tmem);
+    sh_fill_g<PL>(p, s_g);
+    __syncthreads();
+    const int n_virtual = p.n_frames * p.n_groups;
+    for (int vb = blockIdx.x; vb < n_virtual; vb += gridDim.x) sh_pilot_item<PL>(p, row, s_g, s_tiles, &s_last, vb, p.first_sym);
+    tmem_free_cols(s_tmem, kShTmemCols, (int)(threadIdx.x >> 5));
+}
+
+// ---- both in one launch: pilot and data items on one ticket counter -------------------------------------------------
+// The persistent CTAs draw BOTH kinds of item from one counter: first the pilot items of every frame (frame-major), then the
+// data items.  Compared with the kernel pair there is no drain / launch / ramp between the two phases -- CTAs that run out of
+// pilot items start on the data items of the first frames while the last pilot items are still running.  A data item waits
+// (one thread, acquire loads) until the pilot of its frame(s) has signalled completion -- ready[f] = number of this launch,
+// written with release semantics by the CTA that completed frame f.  Every pilot item has a smaller ticket than every data
+// item, i.e. is running or done on a resident CTA, and pilot items never wait: the kernel cannot deadlock whatever the grid
+// size.  The launch number lives on the device next to the counter (ticket[2], advanced by the last CTA to leave), so a
+// launch carries no host-side state.  Channel rows and sum|H|^2 are read around L1 (bulk copies, ld.cg): other CTAs of the
+// same launch write them.
+// Measured and rejected: INTERLEAVING pilot items of later frames with the data items of earlier ones (the pilot work is
+// DRAM-bound, the data work is not, so they looked like they would overlap).  The data items are latency-bound with one row
+// of prefetch; the extra DRAM traffic next to them raises their bulk-copy waits more than the overlap saves (c4, 192 frames:
+// 5.03 ms pilots first, 5.35-5.8 ms interleaved with 50 / 32 / 16 / 8 frames of lead; the kernel pair 5.19 ms).
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <class PL, int MINB>
+__global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_frames_sh(const KernelParams p)
+{
+    constexpr int N = PL::N, TEAMS = PL::TEAMS;
+    static_assert(PL::SH > 1 && PL::ROW == PL::T && PL::THREADS == 128, "shuffle-stage plans only");
+    extern __shared__ __align__(16) float2 smem[];
+    float2* s_h = smem;                     // data items: [TEAMS][N] conj(H) of the current antenna; pilot items: [N] LS-divide table
+    float2* s_tiles = s_h + TEAMS * N;      // [TEAMS][32][T]
+    __shared__ __align__(8) uint64_t bar_x[TEAMS], bar_h[TEAMS];
+    __shared__ unsigned int s_readers[TEAMS];
+    __shared__ long long s_ticket;
+    __shared__ uint32_t s_tmem;
+    __shared__ unsigned int s_last;
+    ShRow<PL> row;
+    sh_setup<PL>(p, row, s_tiles, bar_x, bar_h, s_readers, &s_tmem);
+    const unsigned int epoch = (unsigned int)__ldcg(p.ticket + 2) + 1u;  // (every CTA reads it before the last one to leave advances it)
+    __syncthreads();
+
+    const long long np = (long long)p.n_frames * p.n_groups;  // pilot items, frame-major
+    const long long n_work = (long long)p.n_frames * p.n_sym_work;
+    const long long nd = (n_work + TEAMS - 1) / TEAMS;         // data items
+    const long long n_tickets = np + nd;
+    bool g_valid = false;  // the LS-divide table sits where data items keep their channel rows
+    uint32_t h_phase = 0;
+    for (;;) {
+        const long long tk = draw_ticket(p, n_tickets, &s_ticket, true, [](long long) {});
+        if (tk < 0) break;
+        const long long pilot = tk < np ? tk : -1, data = tk - np;
+        if (pilot >= 0) {
+            if (!g_valid) {
+                sh_fill_g<PL>(p, s_h);
+                g_valid = true;
+                __syncthreads();
+            }
+            const bool completed = sh_pilot_item<PL>(p, row, s_h, s_tiles, &s_last, (int)pilot, 0);
+            if (completed) {
+                __threadfence();   // every thread's channel rows / energy sums, then the flag
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    fence_proxy_async_all();
+                    st_release_gpu(p.ready + pilot / p.n_groups, epoch);
+                }
+            }
+        } else {
+            // the frames of this item's (frame, symbol) pairs: first and last differ at most by one
+            const long long w0 = data * TEAMS, w1 = (w0 + TEAMS - 1 < n_work ? w0 + TEAMS - 1 : n_work - 1);
+            const int f0 = (int)(w0 / p.n_sym_work), f1 = (int)(w1 / p.n_sym_work);
+            if (threadIdx.x == 0) {
+                while (ld_acquire_gpu(p.ready + f0) != epoch) __nanosleep(200);
+                while (ld_acquire_gpu(p.ready + f1) != epoch) __nanosleep(200);
+            }
+            __syncthreads();
+            fence_proxy_async_all();  // the channel rows are fetched by bulk copies (async proxy)
+            g_valid = false;
+            sh_data_item<PL, true>(p, row, s_h + row.team * N, &bar_h[row.team], h_phase, (int)data);
+            __syncthreads();  // (a pilot item may follow and rebuild its table over the channel rows of slower teams)
+        }
+    }
+    tmem_free_cols(s_tmem, kShTmemCols, (int)(threadIdx.x >> 5));
 }
 
 // ---- stand-alone per-step kernels: the individually callable steps of gpuLS.cuh:87-99 -----------

@@ -250,6 +250,12 @@ int lsmrc_sync(lsmrc_handle h);
 int lsmrc_set_oneshot(lsmrc_handle h, int enabled);
 /* whole-frame calls served by the one-launch kernel so far */
 long long lsmrc_oneshot_count(lsmrc_handle h);
+/* 2048- and 4096-point receivers, batches of whole frames large enough to fill the GPU: the channel estimate and the data
+ * symbols run as ONE persistent launch whose CTAs draw first the pilot work, then the data work from one counter (no drain
+ * and ramp between the two phases; data work waits per frame on a device-side ready flag).  Results are
+ * bit-identical to the kernel pair.  enabled = 0 forces the pair; the count says how many calls took the single launch. */
+int lsmrc_set_one_launch_frames(lsmrc_handle h, int enabled);
+long long lsmrc_one_launch_frames_count(lsmrc_handle h);
 
 /* ---- instrumentation (replaces the clock() timers of ShMemSymBuff_gpu.hpp:113-257) --- */
 /* CUDA-event time of the pilot and data kernels of the most recent lsmrc_demod_frames_device

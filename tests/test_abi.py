@@ -93,3 +93,4 @@ def test_reference_gpu_driver_compiles_unmodified_against_the_drop_in_headers():
     nm = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
     for sym in ("lsmrc_first_vector", "lsmrc_demod_one_symbol", "lsmrc_set_pilot_file"):
         assert sym in nm, f"the reference driver does not reach the C ABI through {sym}"
+

@@ -313,6 +313,56 @@ def test_many_frames_through_the_persistent_kernels(ofdm, oracle, dims):
         pytest.fail(f"{n_diff} demapped bits differ (closest oracle symbol is {threshold_margin(ref['combined'], b):.3e} from a threshold)")
 
 
+# (A, N, C, S, b, F): at least one full wave of data items (444 CTAs x teams), so the 2048/4096-point plans take the
+# single launch; the third case has several antenna groups per frame, the fourth an odd prefix (no bulk copies)
+ONE_LAUNCH = [(2, 4096, 288, 4, 6, 160), (3, 2048, 144, 8, 4, 140), (32, 4096, 288, 4, 6, 150), (2, 4096, 33, 3, 2, 230),
+              (4, 2048, 144, 14, 4, 80)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", ONE_LAUNCH)
+def test_single_launch_frames_equal_the_kernel_pair(ofdm, oracle, dims):
+    """2048/4096 points, large batches: pilot and data items come from ONE persistent launch (lsmrc_frames_sh; data items
+    wait on per-frame ready flags written by the pilot items).  Same arithmetic in the same order as the kernel pair, so
+    the outputs must be bit-identical to it -- and match the oracle; repeated calls reuse the device-side launch number."""
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    d = ofdm.synth.make_frames(F, A, N, C, S, b, snr_db=SNR[b], seed=91)
+    dev = torch.device("cuda:0")
+    rx = torch.view_as_real(torch.from_numpy(d["rx"]).to(dev)).contiguous()
+
+    def run(r, want_h):
+        comb = torch.zeros((F, S - 1, K, 2), device=dev)
+        bits = torch.zeros((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+        hc = torch.zeros((F, A, K, 2), device=dev) if want_h else None
+        hs = torch.zeros((F, K), device=dev) if want_h else None
+        torch.cuda.synchronize()   # the fills run on torch's stream, the receiver on its own
+        r.demod_frames_device(rx, F, comb, bits, hc, hs)
+        r.sync()
+        return comb, bits, hc, hs
+
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(d["pilot_asc"])
+        one = [run(r, True), run(r, False), run(r, True)]          # three launches: the launch number advances on the device
+        assert r.one_launch_frames_count() == 3
+        r.set_one_launch_frames(False)
+        pair = run(r, True)
+        assert r.one_launch_frames_count() == 3
+    for got in one:
+        for x, y in zip(got, pair):
+            if x is not None:
+                assert torch.equal(x, y)
+    ref = oracle.demod_frames(d["rx"], d["pilot_asc"], b, C)
+    comb, bits, hc, hs = one[0]
+    assert_close(torch.view_as_complex(hc).cpu().numpy(), ref["hconj"], "Hconj")
+    assert_close(hs.cpu().numpy(), ref["hsqrd"], "sum|H|^2")
+    assert_close(torch.view_as_complex(comb).cpu().numpy(), ref["combined"], "combined")
+    assert_bits_match(bits.cpu().numpy(), ref["bits"], ref["combined"], b, f"{dims} one launch",
+                      got_combined=torch.view_as_complex(comb).cpu().numpy())
+
+
 # ---- BASELINE configs c2, c3, c4 at their FULL dimensions (cpuLS_main.cpp:80-93 is the loop to match) ---------------
 FULL = {
     "c2_full": "c2_full_A64_N1024_C64_S101_16qam",

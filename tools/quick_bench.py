@@ -32,6 +32,8 @@ bits = torch.empty((F, cfg.n_sym - 1, cfg.bits_row_bytes), device=dev, dtype=tor
 r = m.LsMrcReceiver.from_config(cfg, max_frames=1)
 r.set_pilot(m.synth.make_pilot(cfg.K, 1))
 r.set_timing(True)
+if os.environ.get("LSMRC_ONE_LAUNCH") == "0":
+    r.set_one_launch_frames(False)
 print(r.describe_plan())
 for it in range(args.iters):
     r.demod_frames_device(rx, F, comb, bits)
