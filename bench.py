@@ -278,6 +278,7 @@ def scaling_c4_leg(m, dev, local, rank, world, dist, peak, frames=512, steps=5, 
         ms = e0.elapsed_time(e1)
         p_ms, d_ms = r.kernel_ms_history(steps)
         plan = r.describe_plan()
+        n_one = r.one_launch_frames_count()
         r.set_stream(None)
     # every decoded frame against the transmitted bits (the repeated frames against the source of their original)
     want = torch.from_numpy(m.synth.pack_bits_rows(src.cpu().numpy(), cfg.qam_bits)).to(dev)
@@ -324,6 +325,8 @@ def scaling_c4_leg(m, dev, local, rank, world, dist, peak, frames=512, steps=5, 
             "value": world * frames * steps * cfg.antenna_samples_per_frame / (ms_max * 1e-3), "unit": UNIT,
             "algorithmic_gbs_per_gpu": per_gpu_gbs, "frac_of_hbm_peak": per_gpu_gbs / peak,
             "pilot_kernel_ms": statistics.mean(p_ms), "data_kernel_ms": statistics.mean(d_ms),
+            "kernels": "one persistent launch (pilot items, then data items): the whole step is data_kernel_ms" if n_one > 0
+                       else "pilot kernel + data kernel",
             "differing_bit_bytes_vs_source_all_ranks": int(t[1].item()) if dist is not None else errs,
             "frames_checked_per_gpu": frames, "plan": plan, "bits_gather": gather}
 
