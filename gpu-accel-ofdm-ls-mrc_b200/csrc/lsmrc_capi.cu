@@ -368,8 +368,10 @@ PlanOps make_ops()
 // x prefetched to L2, rows of Hconj prefetched to L1, register prefetch of the next row, x through L1, Hconj ring,
 // x rows by bulk copy, stage-1 twiddles in tensor memory, lanes of the shuffle stage.  Each setting is the measured
 // winner of its A/B (DESIGN.md section 3 keeps the log, including the variants that lost and were deleted).
-using Plan64 = Plan<64, 16, 4, 1, 32, 2, 0, 0, 1>;
-using Plan128 = Plan<128, 16, 8, 1, 16, 2, 0, 0, 1>;
+// (64 points: 8 threads x 8 points per row.  16 x 4 -- teams of 4 threads reading 32 contiguous bytes per load, 8 lines per
+// warp request -- measured 13-17 % slower: c1 3.15 -> 3.6 TB/s, 16 antennas 3.7 -> 4.3, 64 antennas 3.9 -> 4.6)
+using Plan64 = Plan<64, 8, 8, 1, 16, 2, 0, 0, 1>;
+using Plan128 = Plan<128, 16, 8, 1, 16, 2, 0, 0, 1>;  // (8 x 4 x 4, three stages with 128-byte team loads: 25-30 % slower)
 using Plan256 = Plan<256, 16, 16, 1, 8, 2, 0, 1, 1>;
 using Plan512 = Plan<512, 32, 16, 1, 8, 1, 1, 1>;  // (tensor-memory twiddles measured 10 % slower here: teams of 16 threads)
 using Plan1024 = Plan<1024, 32, 32, 1, 4, 1, 0, 1, 0, false, true, true, true>;
