@@ -38,17 +38,24 @@ for cfg, frames in FRAMES.items():
     rep = os.path.join(go, f"r02_final_{cfg}.ncu-rep")
     if not os.path.exists(rep):
         continue
-    with open(os.path.join(out, f"r02_ncu_{cfg}.txt"), "w") as f:
-        f.write(f"round 2, config {cfg}: ncu --set full --clock-control none --import-source on -k regex:lsmrc_ -s 2 -c 2 "
-                f"python tools/quick_bench.py --config {cfg} --frames {frames} --iters 2\n"
-                "(launch 0 = pilot kernel, launch 1 = data kernel; numbers under the profiler are not bench values)\n\n")
-        f.write(run("ncu_summary.py", rep))
-        for sec in (1, 0):
-            f.write("\n---- executed warp-instructions per opcode ----\n" + run("ncu_opmix.py", rep, str(sec)))
-        f.write("\n---- top stall instructions of the data kernel (SASS) ----\n" + run("ncu_hotspots.py", rep, "1", "25"))
     k = dram(rep)
-    traffic[cfg] = {"frames": frames, "pilot_kernel": k[0][0][:60], "pilot_kernel_dram_bytes": k[0][1],
-                    "data_kernel": k[1][0][:60], "data_kernel_dram_bytes": k[1][1],
-                    "source": f"profiles/r02_ncu_{cfg}.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch each)"}
+    single = len(k) == 1  # 2048/4096 points: pilot and data items in one persistent launch (lsmrc_frames_sh)
+    with open(os.path.join(out, f"r02_ncu_{cfg}.txt"), "w") as f:
+        f.write(f"round 2, config {cfg}: ncu --set full --clock-control none --import-source on -k regex:lsmrc_ -s {1 if single else 2} "
+                f"-c {1 if single else 2} python tools/quick_bench.py --config {cfg} --frames {frames} --iters 2\n"
+                + ("(one launch: pilot items, then data items, lsmrc_frames_sh" if single else "(launch 0 = pilot kernel, launch 1 = data kernel")
+                + "; numbers under the profiler are not bench values)\n\n")
+        f.write(run("ncu_summary.py", rep))
+        for sec in ((0,) if single else (1, 0)):
+            f.write("\n---- executed warp-instructions per opcode ----\n" + run("ncu_opmix.py", rep, str(sec)))
+        f.write("\n---- top stall instructions of the " + ("" if single else "data ") + "kernel (SASS) ----\n"
+                + run("ncu_hotspots.py", rep, "0" if single else "1", "25"))
+    if single:
+        traffic[cfg] = {"frames": frames, "kernel": k[0][0][:60], "kernel_dram_bytes": k[0][1],
+                        "source": f"profiles/r02_ncu_{cfg}.txt (dram__bytes_read.sum + dram__bytes_write.sum, the single launch)"}
+    else:
+        traffic[cfg] = {"frames": frames, "pilot_kernel": k[0][0][:60], "pilot_kernel_dram_bytes": k[0][1],
+                        "data_kernel": k[1][0][:60], "data_kernel_dram_bytes": k[1][1],
+                        "source": f"profiles/r02_ncu_{cfg}.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch each)"}
 json.dump(traffic, open(os.path.join(out, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
