@@ -94,7 +94,11 @@ int lsmrc_set_pilot_file(lsmrc_handle h, const char *path);
 /* ---- whole frames, device-resident (replaces gpuLS::demodOneFrameCUDA gpuLS.cu:575 /
  *      demodOptimized :677 / demodCuBlas :771).  All pointers are DEVICE pointers.
  *      d_hconj / d_hsqrd / d_bits may be NULL (internal scratch / skipped).  The work is
- *      enqueued on the handle's compute stream; call lsmrc_sync() before reading. ------ */
+ *      enqueued on the handle's compute stream; call lsmrc_sync() before reading.  That
+ *      stream is the handle's own NON-BLOCKING stream unless lsmrc_set_stream was called: it
+ *      does not order against the legacy default stream, so work the caller still has in flight
+ *      on the buffers elsewhere (a fill of the outputs, the upload of d_rx) must have finished,
+ *      or the caller passes its own stream with lsmrc_set_stream and enqueues everything there. */
 int lsmrc_demod_frames_device(lsmrc_handle h, const void *d_rx, int n_frames, void *d_hconj,
                               void *d_hsqrd, void *d_combined, void *d_bits);
 

@@ -240,6 +240,7 @@ def test_wire_format_conversion_alone(ofdm):
             scale = np.float32(1.0 / 32767.0)
             d_in = torch.from_numpy(iq).to(dev)
             d_out = torch.full((rows, max(n_out, 1), 2), -7.0, device=dev)
+            torch.cuda.synchronize()   # the copy and the fill run on torch's stream, the receiver on its own
             r.sc16_to_fc32_device(d_in, rows, n_in, skip, n_out, scale, d_out)
             r.sync()
             got = d_out.cpu().numpy()
