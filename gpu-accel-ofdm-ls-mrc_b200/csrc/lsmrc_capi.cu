@@ -217,6 +217,14 @@ cudaError_t prepare_impl(int* data_ctas_per_sm, int* pilot_ctas_per_sm)
     // (tensor-memory columns per CTA: 2P for the stage-1 twiddles, power of two >= 32)
     e = occupancy_with_tmem(data_ctas_per_sm, lsmrc_kernel<PL, MODE_DATA, MINB>, PL::THREADS, PL::SMEM_BYTES, PL::TW_TMEM ? 2 * PL::P : 0);
     if (e != cudaSuccess) return e;
+    if constexpr (PL::X_TMA && PL::H_RING) {  // the bulk-copy instantiation of the data kernel shares the persistent grid size
+        e = cudaFuncSetAttribute(lsmrc_kernel<PL, MODE_DATA, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int xt = 0;
+        e = occupancy_with_tmem(&xt, lsmrc_kernel<PL, MODE_DATA, MINB, true>, PL::THREADS, PL::SMEM_BYTES, PL::TW_TMEM ? 2 * PL::P : 0);
+        if (e != cudaSuccess) return e;
+        if (xt < *data_ctas_per_sm) *data_ctas_per_sm = xt;
+    }
     if constexpr (PL::SH > 1) {
         // shuffle-stage plans: large batches run the dedicated data kernel (the generic one serves the antenna-split
         // launches of tiny batches); both share the persistent grid size
@@ -301,6 +309,12 @@ cudaError_t launch_impl(int mode, const KernelParams& p, cudaStream_t st, int ma
         if constexpr (PL::SH > 1) {
             if (q.ant_split == 1) {
                 lsmrc_data_sh<PL, MINB><<<grid, PL::THREADS, data_sh_smem<PL>(), st>>>(q);
+                return cudaGetLastError();
+            }
+        }
+        if constexpr (PL::X_TMA && PL::H_RING) {
+            if (q.x_tma) {  // rows 16-byte aligned: the instantiation that brings them in by bulk copy
+                lsmrc_kernel<PL, MODE_DATA, MINB, true><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(q);
                 return cudaGetLastError();
             }
         }

@@ -861,7 +861,9 @@ __device__ __forceinline__ void mrc_finish(const KernelParams& p, const float2 (
     else finish(std::integral_constant<int, 6>{});
 }
 
-template <class PL, int MODE, int MINB>
+// XT (data mode of X_TMA plans): antenna rows come in by bulk copy.  A compile-time switch, not a test of p.x_tma inside the
+// row loop: with both paths in one loop body ptxas schedules the common one 2 % slower (c2: 2.42 -> 2.36 ms per 256 frames).
+template <class PL, int MODE, int MINB, bool XT = false>
 __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelParams p)
 {
     constexpr int N = PL::N, P = PL::P, T = PL::T, K = N - 1;
@@ -1284,7 +1286,8 @@ __global__ void __launch_bounds__(PL::THREADS, MINB) lsmrc_kernel(const KernelPa
         if (PL::REG_PF != 0) row_load<PL>(v, x0 + (long long)(aj < p.n_ant ? aj : p.n_ant - 1) * p.ant_stride, t);  // this team's first antenna
         // X_TMA: row a of this team's symbol arrives in the team's tile by bulk copy; row 0 is requested here,
         // row a+1 from inside row a (see the hook below).  x_tma is off when rows are not 16-byte aligned.
-        const bool x_tma = PL::X_TMA && p.x_tma && AS == 1;  // (with the antenna split rows are not consecutive)
+        static_assert(!XT || (PL::X_TMA && PL::H_RING), "bulk-copied rows: X_TMA plans whose teams never split a pair's antennas");
+        constexpr bool x_tma = XT;  // (the launcher picks the instantiation: rows 16-byte aligned or not)
         if (PL::X_TMA && x_tma && t == 0) {
             fence_proxy_async();  // the tile doubled as the previous item's demap byte buffer
             mbar_expect_tx(&bar_x[team], ROW_BYTES);
