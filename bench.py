@@ -223,17 +223,20 @@ def h2d_ceiling(dev, nbytes, dist, world, reps=10):
 
     once()
     torch.cuda.synchronize(dev)
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        once()
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return world * 3 * n * reps / float(t.item()) / 1e9
+    best = 0.0
+    for _ in range(3):  # a ceiling: the best of three trials (a single trial is now and then 5 % low)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = max(best, world * 3 * n * reps / float(t.item()) / 1e9)
+    return best
 
 
 def scaling_c4_leg(m, dev, local, rank, world, dist, peak, frames=512, steps=5, warmup=2, unique=64):
