@@ -384,7 +384,8 @@ PlanOps make_ops()
 // winner of its A/B (DESIGN.md section 3 keeps the log, including the variants that lost and were deleted).
 // (64 points: 8 threads x 8 points per row.  16 x 4 -- teams of 4 threads reading 32 contiguous bytes per load, 8 lines per
 // warp request -- measured 13-17 % slower: c1 3.15 -> 3.6 TB/s, 16 antennas 3.7 -> 4.3, 64 antennas 3.9 -> 4.6)
-using Plan64 = Plan<64, 8, 8, 1, 16, 2, 1, 1, 0>;  // (next sample row prefetched to L2, next channel row to L1: +1..4 % over the register prefetch)
+using Plan64 = Plan<64, 8, 8, 1, 8, 2, 1, 1, 0>;  // (next sample row prefetched to L2, next channel row to L1: +1..4 % over the register prefetch;
+                                                  // 8 teams per CTA: the pilot kernel of 16-antenna frames 0.042 -> 0.034 ms, the rest +-1 %)
 using Plan128 = Plan<128, 16, 8, 1, 16, 2, 0, 0, 1>;  // (8 x 4 x 4, three stages with 128-byte team loads: 25-30 % slower; L2/L1 prefetches: -1..-9 %)
 using Plan256 = Plan<256, 16, 16, 1, 8, 2, 1, 1, 1>;  // (+ L2 prefetch of the sample row after next: +7 %)
 using Plan512 = Plan<512, 32, 16, 1, 8, 1, 1, 1>;  // (tensor-memory twiddles measured 10 % slower here: teams of 16 threads)
