@@ -98,7 +98,11 @@ int lsmrc_set_pilot_file(lsmrc_handle h, const char *path);
  *      stream is the handle's own NON-BLOCKING stream unless lsmrc_set_stream was called: it
  *      does not order against the legacy default stream, so work the caller still has in flight
  *      on the buffers elsewhere (a fill of the outputs, the upload of d_rx) must have finished,
- *      or the caller passes its own stream with lsmrc_set_stream and enqueues everything there. */
+ *      or the caller passes its own stream with lsmrc_set_stream and enqueues everything there.
+ *      On the caller's stream a call can also be captured into a CUDA graph and replayed (after one
+ *      ordinary call of the same size, which allocates the per-frame channel state): the kernels
+ *      keep their work counters on the device and re-arm them themselves, nothing is mirrored on
+ *      the host (tests/test_gpu_parity.py::test_device_calls_replay_from_a_cuda_graph). */
 int lsmrc_demod_frames_device(lsmrc_handle h, const void *d_rx, int n_frames, void *d_hconj,
                               void *d_hsqrd, void *d_combined, void *d_bits);
 

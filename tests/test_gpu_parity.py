@@ -456,3 +456,53 @@ def test_caller_stream_orders_the_launches_and_null_returns_to_the_own_stream(of
                 out = comb.cpu()
             assert_close(torch.view_as_complex(out).numpy(), ref["combined"], f"combined (user stream: {use_user})")
             assert np.array_equal(bits.cpu().numpy(), ref["bits"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(6, 1024, 64, 5, 4, 140), (2, 4096, 288, 4, 6, 160), (4, 64, 16, 16, 2, 300)])
+def test_device_calls_replay_from_a_cuda_graph(ofdm, dims):
+    """The persistent kernels keep their work counters (and the single-launch kernel its launch number and ready flags) on the
+    device and re-arm them themselves, so a captured call can be replayed: capture lsmrc_demod_frames_device on the caller's
+    stream once, replay it on three different inputs, and compare each replay with an ordinary call on the same input."""
+    import torch
+
+    A, N, C, S, b, F = dims
+    K = N - 1
+    dev = torch.device("cuda:0")
+    user = torch.cuda.Stream(dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    inputs = [torch.randn((F, S, A, N + C, 2), device=dev, generator=g) for _ in range(3)]
+    rx = torch.empty_like(inputs[0])
+    comb = torch.zeros((F, S - 1, K, 2), device=dev)
+    bits = torch.zeros((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+    hs = torch.zeros((F, K), device=dev)
+    torch.cuda.synchronize(dev)
+    with ofdm.LsMrcReceiver(A, N, C, S, b) as r:
+        r.set_pilot(ofdm.synth.make_pilot(K, 3))
+        r.set_oneshot(0)
+        r.set_stream(user.cuda_stream)
+        with torch.cuda.stream(user):
+            rx.copy_(inputs[0])
+            r.demod_frames_device(rx, F, comb, bits, None, hs)        # first call: channel state allocated outside the capture
+        user.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=user):
+            r.demod_frames_device(rx, F, comb, bits, None, hs)
+        for x in inputs:
+            with torch.cuda.stream(user):
+                rx.copy_(x)
+                comb.zero_()
+                bits.zero_()
+                hs.zero_()
+                graph.replay()
+            user.synchronize()
+            got = (comb.clone(), bits.clone(), hs.clone())
+            with torch.cuda.stream(user):
+                comb.zero_()
+                bits.zero_()
+                hs.zero_()
+                r.demod_frames_device(rx, F, comb, bits, None, hs)
+            user.synchronize()
+            assert torch.equal(got[0], comb) and torch.equal(got[1], bits) and torch.equal(got[2], hs)
+            assert bool(torch.isfinite(comb).all()) and float(comb.abs().max()) > 0
+        r.set_stream(None)
