@@ -506,3 +506,59 @@ def test_device_calls_replay_from_a_cuda_graph(ofdm, dims):
             assert torch.equal(got[0], comb) and torch.equal(got[1], bits) and torch.equal(got[2], hs)
             assert bool(torch.isfinite(comb).all()) and float(comb.abs().max()) > 0
         r.set_stream(None)
+
+
+@pytest.mark.gpu
+def test_two_receivers_on_one_gpu_from_two_threads(ofdm):
+    """One handle per thread is the contract (a handle is single-threaded).  Two receivers -- a 4096-point one on the
+    single-launch kernel, whose data items wait for pilot items of the same launch, and a 1024-point one on the kernel pair --
+    run concurrently on one GPU from two host threads; both kinds of persistent kernel then share the SMs, neither may stall
+    the other for good, and every result must equal the one computed alone."""
+    import threading
+
+    import torch
+
+    dev = torch.device("cuda:0")
+    cases = [(2, 4096, 288, 4, 6, 160), (6, 1024, 64, 5, 4, 140)]
+    state = []
+    for A, N, C, S, b, F in cases:
+        K = N - 1
+        g = torch.Generator(device=dev).manual_seed(N)
+        rx = torch.randn((F, S, A, N + C, 2), device=dev, generator=g)
+        comb = torch.zeros((F, S - 1, K, 2), device=dev)
+        bits = torch.zeros((F, S - 1, (K * b + 7) // 8), device=dev, dtype=torch.uint8)
+        r = ofdm.LsMrcReceiver(A, N, C, S, b)
+        r.set_pilot(ofdm.synth.make_pilot(K, 2))
+        r.set_oneshot(0)
+        state.append((r, rx, F, comb, bits))
+    torch.cuda.synchronize(dev)
+    try:
+        alone = []
+        for r, rx, F, comb, bits in state:
+            r.demod_frames_device(rx, F, comb, bits)
+            r.sync()
+            alone.append((comb.clone(), bits.clone()))
+        errors = []
+
+        def work(i):
+            r, rx, F, comb, bits = state[i]
+            try:
+                for _ in range(12):
+                    r.demod_frames_device(rx, F, comb, bits)
+                r.sync()
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(state))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+        assert not any(t.is_alive() for t in threads), "a receiver did not finish: the two persistent kernels block each other"
+        assert not errors, errors
+        for (r, rx, F, comb, bits), (c0, b0) in zip(state, alone):
+            assert torch.equal(comb, c0) and torch.equal(bits, b0)
+        assert state[0][0].one_launch_frames_count() == 13
+    finally:
+        for r, *_ in state:
+            r.close()
